@@ -1,0 +1,5 @@
+from .buffers import (CudaFastQBuffer, CudaTwoLineFastaBuffer, CudaOneLineBuffer, FastQBuffer, TwoLineFastaBuffer,
+                      FieldView)
+from .exceptions import FormatException, IncompleteEntryException
+from .files import bnp_open
+from .parser import CudaFileReader, NpDataclassReader

@@ -1,0 +1,139 @@
+"""get_kmers / count_kmers (mirror of bionumpy/sequence/kmers.py:36-145).
+
+Hash definition (pinned against the reference's doc goldens): h = sum_j code[i+j] * 4^j, int64,
+per-row windows only, rows shorter than k give empty rows.  ``get_kmers`` returns a lazily
+materialised EncodedRaggedArray: asking for ``.raw()``/indexing runs the hash kernel (K3);
+``count_encoded(kmers, axis=None)`` runs the fused hash+histogram kernel instead and never
+writes the hashes."""
+import logging
+
+import torch
+
+from .. import _native as nv
+from .. import config, ops
+from ..encoded_array import EncodedArray, EncodedRaggedArray, BaseEncoding
+from ..encodings.alphabet_encoding import AlphabetEncoding, DNAEncoding
+from ..encodings.exceptions import EncodingError
+from ..encodings.kmer_encodings import KmerEncoding
+from ..streams import streamable
+from .count_encoded import count_encoded, count_hashed, EncodedCounts
+
+logger = logging.getLogger(__name__)
+
+
+class _Source:
+    """The ragged byte view a lazy value array is computed from."""
+
+    def __init__(self, base, starts, lens, enc_mode, lut, alphabet_encoding, chunk_buffer=None):
+        self.base, self.starts, self.lens = base, starts, lens
+        self.enc_mode, self.lut, self.alphabet_encoding = enc_mode, lut, alphabet_encoding
+        self.chunk_buffer = chunk_buffer     # set when the view is an untouched field of a file buffer
+
+
+def _source_of(sequence) -> _Source:
+    if isinstance(sequence, EncodedArray):
+        assert sequence.ndim == 1, "only 1-D EncodedArray and EncodedRaggedArray are supported"
+        data = sequence.raw().contiguous()
+        starts = torch.zeros(1, dtype=torch.int64, device=data.device)
+        lens = torch.full((1,), data.numel(), dtype=torch.int32, device=data.device)
+    else:
+        data = sequence._data.contiguous()
+        starts, lens = sequence._starts.contiguous(), sequence._lens.contiguous()
+    if not data.is_cuda:
+        raise nv.NativeLibraryError("k-mer kernels need CUDA tensors: bionumpy_b200 has no CPU fallback")
+    if data.dtype != torch.uint8:
+        data = data.to(torch.uint8)
+    enc = sequence.encoding
+    if enc.is_base_encoding():
+        target = DNAEncoding                                    # kmers.py:70-72
+        return _Source(data, starts, lens, target.enc_mode, None, target,
+                       getattr(sequence, "_chunk_buffer", None))
+    assert isinstance(enc, AlphabetEncoding), \
+        "Sequence needs to be encoded with an AlphabetEncoding, e.g. DNAEncoding. " \
+        "Change encoding of your sequences by using e.g. bnp.change_encoding(sequences, bnp.DNAEncoding)"
+    if enc.alphabet_size != 4:
+        raise NotImplementedError("only 4-letter alphabets are on the CUDA k-mer path "
+                                  "(the reference's generic dot-product path, kmers.py:87, is out of scope)")
+    return _Source(data, starts, lens, nv.ENC_CODES, None, enc)
+
+
+class LazyKmerValues(EncodedRaggedArray):
+    """EncodedRaggedArray of k-mer hashes / minimizers whose int64 data appear on first use."""
+
+    def __init__(self, source: _Source, k: int, window_size: int, flat_input: bool = False):
+        self._source, self._k, self._window = source, k, window_size
+        shrink = (window_size if window_size else k) - 1
+        self._lens = torch.clamp(source.lens - shrink, min=0).to(torch.int32)
+        ends = torch.cumsum(self._lens.to(torch.int64), 0)
+        self._starts = ends - self._lens
+        self._contiguous = True
+        self._encoding = KmerEncoding(source.alphabet_encoding, k)
+        self._lazy = None
+        self._flat_input = flat_input
+
+    # RaggedArray keeps its flat data in ``_data``; here it is computed on demand
+    @property
+    def _data(self):
+        if self._lazy is None:
+            s = self._source
+            shrink = (self._window if self._window else self._k) - 1
+            offsets = ops.row_offsets(s.lens, shrink)
+            if self._window:
+                vals, _, status = ops.rows_minimizers(s.base, s.starts, s.lens, s.enc_mode, self._k, self._window,
+                                                      s.lut, offsets)
+            else:
+                vals, _, status = ops.rows_kmer_hash(s.base, s.starts, s.lens, s.enc_mode, self._k, s.lut, offsets)
+            self._check(status)
+            self._lazy = vals
+        return self._lazy
+
+    @_data.setter
+    def _data(self, v):
+        self._lazy = v
+
+    def is_materialised(self):
+        return self._lazy is not None
+
+    def _check(self, status):
+        bad = ops.read_status(status).bad_base()
+        if bad is not None:
+            logging.error("Tried to change encoding of sequences to DNAEncoding, but failed. "
+                          "Make sure your sequences are valid DNA, only containing A, C, G, and T")
+            self._source.alphabet_encoding._raise_encoding_error(bad[0], bad[1], self._source.lens)
+
+    def fused_histogram(self, n_bins: int) -> torch.Tensor:
+        """hist[b] = #{values == b (mod n_bins)} without writing the values (K3/K4 + K5 fused)."""
+        s = self._source
+        buf = s.chunk_buffer
+        if buf is not None and buf.can_fuse_count():
+            return buf.fused_kmer_histogram(self._k, self._window, n_bins, s.enc_mode, s.lut)
+        hist, status = ops.rows_kmer_count(s.base, s.starts, s.lens, s.enc_mode, self._k, n_bins, self._window, s.lut)
+        self._check(status)
+        return hist
+
+
+def get_kmers(sequence, k: int):
+    """kmers.py:36-87.  ``sequence``: EncodedRaggedArray / 1-D EncodedArray, BaseEncoding text or an
+    AlphabetEncoding with four letters; k in 1..31."""
+    assert 0 < k < 32, "k must be larger than 0 and smaller than 32"
+    src = _source_of(sequence)
+    out = LazyKmerValues(src, k, 0)
+    if not config.LAZY:
+        out._data
+    if isinstance(sequence, EncodedArray):
+        return EncodedArray(out._data, out.encoding)
+    return out
+
+
+@streamable(sum)
+def count_kmers(sequence, k: int, axis=None) -> EncodedCounts:
+    """kmers.py:129-145."""
+    return count_encoded(get_kmers(sequence, k), axis=axis)
+
+
+def count_kmers_hashed(sequence, k: int, n_buckets: int = 1 << 24, window_size: int = 0) -> torch.Tensor:
+    """EXTENSION: np.bincount(get_kmers(sequence, k) % n_buckets) (or of the minimizers when
+    window_size > 0) as an int64 CUDA tensor, fused."""
+    from .minimizers import get_minimizers
+    vals = get_minimizers(sequence, k, window_size) if window_size else get_kmers(sequence, k)
+    return count_hashed(vals, n_buckets)
