@@ -31,6 +31,8 @@ SIGNATURES = {
     "bnpk_last_error": (ctypes.c_char_p, []),
     "bnpk_sm_count": (_i, []),
     "bnpk_launch_count": (_u64, []),
+    "bnpk_profile_enable": (_i, [_i]),
+    "bnpk_profile_read": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64)]),
     "bnpk_status_init": (_i, [_vp, _vp]),
     "bnpk_count_byte": (_i, [_vp, _sz, _u8, _vp, _vp]),
     "bnpk_tile_workspace_bytes": (_sz, [_sz]),

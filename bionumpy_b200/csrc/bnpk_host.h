@@ -26,6 +26,10 @@ int sm_count();
         if (e__ != cudaSuccess) return ::bnpk::cuda_fail(e__, name); \
     } while (0)
 
+// optional per-launch timing of the dominant (tile) kernel, see bnpk_profile_* in bnpk.h
+void profile_before(cudaStream_t st);
+void profile_after(cudaStream_t st);
+
 size_t tile_workspace_bytes(size_t n);
 bool use_smem_hist(int64_t n_bins, int hist_mode);
 

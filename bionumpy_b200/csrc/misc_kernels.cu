@@ -1,5 +1,8 @@
 // misc_kernels.cu -- byte census, ragged offsets (single-pass scan), standalone bincount,
 // synthetic FASTQ generator, and the small C-ABI entry points.
+#include <mutex>
+#include <utility>
+#include <vector>
 #include "bnpk_host.h"
 
 namespace bnpk {
@@ -16,6 +19,30 @@ int cuda_fail(cudaError_t e, const char *what) {
     cudaGetLastError();
     return (int)e;
 }
+// ---- optional timing of the tile kernel (CUDA events on the launching stream) ----------------
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void profile_before(cudaStream_t st) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    if (!g_prof_on) return;
+    cudaEvent_t a = prof_event(), b = prof_event();
+    cudaEventRecord(a, st);
+    g_prof_events.emplace_back(a, b);
+}
+void profile_after(cudaStream_t st) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    if (!g_prof_on || g_prof_events.empty()) return;
+    cudaEventRecord(g_prof_events.back().second, st);
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -220,6 +247,29 @@ int bnpk_abi_version(void) { return BNPK_ABI_VERSION; }
 const char *bnpk_last_error(void) { return g_err; }
 int bnpk_sm_count(void) { return sm_count(); }
 uint64_t bnpk_launch_count(void) { return g_launches.load(); }
+
+int bnpk_profile_enable(int on) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int bnpk_profile_read(double *total_ms, uint64_t *n_launches) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    double total = 0;
+    uint64_t n = 0;
+    for (auto &p : g_prof_events) {
+        float ms = 0;
+        cudaEventSynchronize(p.second);
+        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) { total += ms; ++n; }
+        g_prof_pool.push_back(p.first);
+        g_prof_pool.push_back(p.second);
+    }
+    g_prof_events.clear();
+    if (total_ms) *total_ms = total;
+    if (n_launches) *n_launches = n;
+    return 0;
+}
 
 int bnpk_status_init(int64_t *status, void *stream) {
     status_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(status);

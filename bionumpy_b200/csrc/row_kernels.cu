@@ -6,6 +6,7 @@
 //   K4 rows_minimizers  get_minimizers             sequence/minimizers.py:20-54
 //   K3/K4+K5 rows_kmer_count   count_kmers         sequence/kmers.py:129-145
 // plus the clean-up passes of the fused chunk count (long rows, trailing incomplete entry).
+#include <climits>
 #include "bnpk_host.h"
 
 namespace bnpk {
@@ -90,7 +91,7 @@ __device__ void warp_row(const RowArgs &a, uint32_t *w_codes, uint32_t *w_flags,
         }
         if (lane < 4) w_codes[n_units + lane] = 0;
         __syncwarp();
-        if (!reported) {
+        if (!reported && !(RM == RM_ENCODE && ENC == BNPK_ENC_LUT)) {
             const int bad = find_invalid(w_flags, off, off + seg_len, lane);
             if (bad >= 0) {
                 reported = true;
@@ -100,9 +101,27 @@ __device__ void warp_row(const RowArgs &a, uint32_t *w_codes, uint32_t *w_flags,
         }
         if constexpr (RM == RM_ENCODE) {
             uint8_t *out = reinterpret_cast<uint8_t *>(a.out) + out_off + seg_start;
-            for (int p = lane; p < seg_len; p += 32) {
-                const int b = off + p;
-                out[p] = (uint8_t)((w_codes[b >> 4] >> (2 * (b & 15))) & 3u);
+            if constexpr (ENC == BNPK_ENC_LUT) {
+                // any alphabet size: the full LUT value is the code, 255 = invalid
+                // (AlphabetEncoding._encode, encodings/alphabet_encoding.py:34-46)
+                int first_bad = INT_MAX;
+                for (int p = lane; p < seg_len; p += 32) {
+                    const uint8_t code = s_lut[a.base[g0 + p]];
+                    out[p] = code;
+                    if (code == 255 && p < first_bad) first_bad = p;
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+                if (first_bad != INT_MAX && !reported) {
+                    reported = true;
+                    if (lane == 0)
+                        atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE], (long long)((r << 32) | (seg_start + first_bad)));
+                }
+            } else {
+                for (int p = lane; p < seg_len; p += 32) {
+                    const int b = off + p;
+                    out[p] = (uint8_t)((w_codes[b >> 4] >> (2 * (b & 15))) & 3u);
+                }
             }
         } else if constexpr (RM == RM_HASH) {
             int64_t *out = reinterpret_cast<int64_t *>(a.out) + out_off + seg_start;

@@ -374,7 +374,9 @@ static int launch_tile(const TileArgs &a, cudaStream_t st) {
     const int64_t n_tiles = a.tile_end - a.tile_begin;
     if (n_tiles <= 0) return 0;
     const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)sm_count() * per_sm);
+    profile_before(st);
     kern<<<(unsigned)grid, kTileThreads, smem, st>>>(a);
+    profile_after(st);
     BNPK_LAUNCHED("tile_kernel");
     return 0;
 }

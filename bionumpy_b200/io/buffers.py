@@ -23,7 +23,7 @@ def _to_device_bytes(chunk):
     if isinstance(chunk, EncodedArray):
         chunk = chunk.raw()
     if isinstance(chunk, np.ndarray):
-        chunk = torch.from_numpy(np.ascontiguousarray(chunk, dtype=np.uint8))
+        chunk = torch.from_numpy(np.array(chunk, dtype=np.uint8, copy=not chunk.flags.writeable))
     if not isinstance(chunk, torch.Tensor):
         chunk = torch.frombuffer(bytearray(chunk), dtype=torch.uint8)
     if not chunk.is_cuda:

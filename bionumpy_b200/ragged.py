@@ -203,7 +203,7 @@ class RaggedArray:
 
     __hash__ = None
 
-    def sum(self, axis=None):
+    def sum(self, axis=None, **kwargs):
         if axis is None:
             return self.ravel().sum()
         if axis in (-1, 1):

@@ -134,6 +134,6 @@ def count_kmers(sequence, k: int, axis=None) -> EncodedCounts:
 def count_kmers_hashed(sequence, k: int, n_buckets: int = 1 << 24, window_size: int = 0) -> torch.Tensor:
     """EXTENSION: np.bincount(get_kmers(sequence, k) % n_buckets) (or of the minimizers when
     window_size > 0) as an int64 CUDA tensor, fused."""
-    from .minimizers import get_minimizers
-    vals = get_minimizers(sequence, k, window_size) if window_size else get_kmers(sequence, k)
-    return count_hashed(vals, n_buckets)
+    assert 0 < k < 32, "k must be larger than 0 and smaller than 32"
+    assert window_size == 0 or k <= window_size, "kmer size must be smaller than window size"
+    return count_hashed(LazyKmerValues(_source_of(sequence), k, window_size), n_buckets)

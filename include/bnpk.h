@@ -209,6 +209,12 @@ int  bnpk_pipeline_kmer_count_host(bnpk_pipeline *ctx, const uint8_t *chunk_host
  * ------------------------------------------------------------------------------------- */
 int bnpk_synth_fastq(uint8_t *out, uint64_t first_record, uint64_t n_records, uint64_t seed, void *stream);
 
+/* Measurement hooks: when enabled, every launch of the dominant (tile) kernel is bracketed by
+ * CUDA events on the launching stream; bnpk_profile_read waits for them, returns the summed
+ * duration and the launch count, and clears the list. */
+int bnpk_profile_enable(int on);
+int bnpk_profile_read(double *total_ms, uint64_t *n_launches);
+
 /* how many kernels this library has launched in this process (bench's gpu_launches) */
 uint64_t bnpk_launch_count(void);
 
