@@ -14,13 +14,13 @@
 
 namespace bnpk {
 
-constexpr int kTileBytes = 32768;          // bytes owned by one tile
+constexpr int kTileBytes = 16384;          // bytes owned by one tile
 constexpr int kHaloBytes = 2048;           // extra bytes staged so in-tile rows can finish
 constexpr int kTileThreads = 512;
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kTileUnits = kTileBytes / 16;                  // 2048
-constexpr int kStagedUnits = (kTileBytes + kHaloBytes) / 16; // 2176
-constexpr int kRowCap = 4096;              // rows handled per round inside a tile
+constexpr int kTileUnits = kTileBytes / 16;                  // 1024
+constexpr int kStagedUnits = (kTileBytes + kHaloBytes) / 16; // 1152
+constexpr int kRowCap = 512;               // rows of one tile kept in shared memory (more: deferred)
 constexpr int kSmemMaxBins = 32768;        // u32 bins that fit next to the tile staging
 
 constexpr uint64_t kFlagAgg = 1ull << 62;
@@ -63,6 +63,8 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
 // tile's aggregate, walks back over predecessors until an inclusive prefix is found, publishes
 // the tile's inclusive prefix and returns the exclusive one.  Tiles are handed out in
 // increasing order by an atomic ticket, so every predecessor is already running (or done).
+// The walk keeps kLookbackDepth windows of 32 predecessors in flight per round trip.
+constexpr int kLookbackDepth = 4;
 __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, int64_t tile, uint64_t aggregate, int lane) {
     if (tile == 0) {
         if (lane == 0) st_relaxed(state, kFlagPrefix | aggregate);
@@ -72,20 +74,45 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, int64_t 
     uint64_t excl = 0;
     int64_t idx = tile - 1;
     while (true) {
-        const int64_t j = idx - lane;
-        uint64_t s;
+        uint64_t s[kLookbackDepth];
+        bool pending;
         do {
-            s = (j >= 0) ? ld_relaxed(state + j) : kFlagPrefix;
-        } while (__any_sync(0xffffffffu, (s >> 62) == 0));
-        const unsigned pmask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-        uint64_t v = s & kValueMask;
-        if (pmask) {
-            const int first = __ffs(pmask) - 1;
-            if (lane > first) v = 0;
+            pending = false;
+#pragma unroll
+            for (int d = 0; d < kLookbackDepth; ++d) {
+                const int64_t j = idx - 32 * d - lane;
+                s[d] = (j >= 0) ? ld_relaxed(state + j) : kFlagPrefix;
+            }
+            // only entries up to the first inclusive prefix matter
+            bool need = true;
+#pragma unroll
+            for (int d = 0; d < kLookbackDepth; ++d) {
+                const unsigned zero = __ballot_sync(0xffffffffu, (s[d] >> 62) == 0);
+                const unsigned pref = __ballot_sync(0xffffffffu, (s[d] >> 62) == 2);
+                if (need) {
+                    // a not-yet-published entry before the first prefix of this window?
+                    const unsigned before = pref ? ((pref & (0u - pref)) - 1u) : 0xffffffffu;   // lanes closer than the first prefix
+                    if (zero & before) pending = true;
+                    if (pref) need = false;
+                }
+            }
+        } while (pending);
+        bool done = false;
+#pragma unroll
+        for (int d = 0; d < kLookbackDepth; ++d) {
+            if (!done) {
+                const unsigned pmask = __ballot_sync(0xffffffffu, (s[d] >> 62) == 2);
+                uint64_t v = s[d] & kValueMask;
+                if (pmask) {
+                    const int first = __ffs(pmask) - 1;
+                    if (lane > first) v = 0;
+                    done = true;
+                }
+                excl += warp_sum_u64(v);
+            }
         }
-        excl += warp_sum_u64(v);
-        if (pmask) break;
-        idx -= 32;
+        if (done) break;
+        idx -= 32 * kLookbackDepth;
     }
     if (lane == 0) st_relaxed(state + tile, kFlagPrefix | ((excl + aggregate) & kValueMask));
     return excl;

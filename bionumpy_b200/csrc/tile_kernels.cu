@@ -1,12 +1,18 @@
 // tile_kernels.cu -- single-pass kernels over raw chunk bytes (K1 line split, K6 fused count).
 //
-// One persistent CTA per resident slot; tiles of kTileBytes are handed out in order by an
-// atomic ticket.  Per tile: coalesced uint4 streaming loads -> in-register byte->(2-bit code,
-// newline, valid) transform -> 8 bytes of shared memory per 16 input bytes; per-tile newline
-// count -> decoupled look-back -> global line index of every newline (the row-offset vector
-// lives in shared memory only); one warp per read row: rolling 2-bit hash read straight from
-// the packed stream, optional warp-shuffle sliding minimum, privatised shared-memory histogram
-// (or global atomics for big tables).
+// Persistent CTAs; tiles of kTileBytes (+ a halo so rows that start in a tile can finish in it)
+// are handed out in order by an atomic ticket.  Thread t of a CTA owns the 64 contiguous bytes
+// [64t, 64t+64) of the staged region (two 256-bit loads); the last warp owns the halo.  Per tile:
+//   1. 64 B/thread -> registers; exact '\n' mask per thread (SWAR zero-byte test)
+//   2. block scan of newline counts + decoupled look-back -> global line index of every byte,
+//      so every thread knows which of its bytes lie on a sequence line (the row-offset vector
+//      never leaves the SM: row starts/ends go to shared memory)
+//   3. only sequence bytes are turned into 2-bit codes (and validated) -> packed stream in smem
+//   4. four threads per read row walk the packed stream: funnel-shift = rolling 2-bit hash,
+//      one shared-memory atomic per k-mer into the CTA-private histogram
+//   5. at the end of the grid-stride loop the private histogram is flushed with global atomics.
+// Minimizers use one warp per row and a warp-shuffle sliding minimum.
+#include <cstdlib>
 #include "bnpk_host.h"
 
 namespace bnpk {
@@ -15,10 +21,9 @@ struct TileArgs {
     const uint8_t *chunk;
     size_t n;
     int64_t tile_begin, tile_end;  // tiles handled by this launch
-    int lpe, field_line, start_offset;
+    int lpe, lpe_shift, field_line, start_offset;
     uint32_t header_char;
     int check_plus;
-    int trim_cr;                   // -1 auto (status[CR]), 0, 1
     int64_t *status;
     uint64_t *ws;                  // header | tile_state[] | deferred[]
     int64_t n_tiles_total;
@@ -30,6 +35,7 @@ struct TileArgs {
     // count
     const uint8_t *lut;
     int k, window;                 // window = 0: k-mers; else minimizers over `window` bases
+    int debug;                     // BNPK_DEBUG env: timing experiments only (results become wrong)
     uint64_t n_bins;
     unsigned long long *hist;
 };
@@ -63,63 +69,121 @@ __global__ void cr_detect_kernel(const uint8_t *chunk, size_t n, int lpe, int tr
     status[BNPK_ST_CR] = cr;
 }
 
-// -------------------------------------------------------------------------------------------
-// block-wide exclusive scan of one uint32 per thread (kTileThreads threads)
-// -------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp, uint32_t &total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
+// 256-bit streaming load (sm_100: LDG.E.256), read-only path, no L1 allocation
+__device__ __forceinline__ void ld_stream_256(const uint8_t *p, uint32_t *r) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
+// exact per-byte "== pattern byte" flags at bit 7 of every byte
+__device__ __forceinline__ uint32_t bytes_eq_msb(uint32_t w, uint32_t pattern) {
+    const uint32_t v = w ^ pattern;
+    return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+// bits 7,15,23,31 -> bits 0..3 (one IMAD.HI: the partial products land on distinct bits)
+__device__ __forceinline__ uint32_t msb_to_nibble(uint32_t z) { return __umulhi(z, 0x02040810u) & 0xFu; }
+
+// 16 flag bits (one per byte) of four words
+__device__ __forceinline__ uint32_t eq_mask16(const uint32_t *w, uint32_t pattern) {
+    const uint32_t n0 = msb_to_nibble(bytes_eq_msb(w[0], pattern)), n1 = msb_to_nibble(bytes_eq_msb(w[1], pattern));
+    const uint32_t n2 = msb_to_nibble(bytes_eq_msb(w[2], pattern)), n3 = msb_to_nibble(bytes_eq_msb(w[3], pattern));
+    return (n1 * 16u + n0) + (n3 * 16u + n2) * 256u;
+}
+__device__ __forceinline__ uint64_t eq_mask64(const uint32_t *raw, uint32_t pattern) {
+    const uint32_t lo = eq_mask16(raw, pattern) | (eq_mask16(raw + 4, pattern) << 16);
+    const uint32_t hi = eq_mask16(raw + 8, pattern) | (eq_mask16(raw + 12, pattern) << 16);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// One 16-byte unit of sequence bytes -> 32 bits of 2-bit codes; `bad` becomes non-zero iff a byte
+// selected by `seq16` is outside the alphabet (exact).
+template <int ENC>
+__device__ __forceinline__ uint32_t encode_unit_seq(const uint32_t *w, uint32_t seq16, const uint8_t *s_lut, uint32_t &bad) {
+    uint32_t codes = 0;
+    if constexpr (ENC == BNPK_ENC_ASCII_ACGT || ENC == BNPK_ENC_ASCII_ACTG) {
+        uint32_t dif[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = lane < kTileWarps ? s_warp[lane] : 0;
-        uint32_t winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
+        for (int j = 0; j < 4; ++j) {
+            uint32_t x;
+            if constexpr (ENC == BNPK_ENC_ASCII_ACGT) x = ((w[j] >> 1) ^ (w[j] >> 2)) & 0x03030303u;
+            else x = (w[j] >> 1) & 0x03030303u;
+            codes |= bytes_2bit_to_byte(x) << (8 * j);
+            // re-decode the codes (PRMT as a 4-entry byte LUT) and compare with the case-folded input
+            const uint32_t y = x | (x >> 4);
+            const uint32_t sel = __byte_perm(y, 0u, 0x4420);       // nibbles = the four codes
+            const uint32_t letters = (ENC == BNPK_ENC_ASCII_ACGT) ? 0x74676361u : 0x67746361u;  // "acgt" / "actg"
+            dif[j] = __byte_perm(letters, 0u, sel) ^ (w[j] | 0x20202020u);
         }
-        if (lane < kTileWarps) s_warp[lane] = winc - w;
-        if (lane == kTileWarps - 1) s_warp[kTileWarps] = winc;
+        if (seq16 == 0xFFFFu) {
+            bad = dif[0] | dif[1] | dif[2] | dif[3];
+        } else {
+            bad = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t nz = (((dif[j] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dif[j]) & 0x80808080u;  // byte != 0
+                bad |= msb_to_nibble(nz) & (seq16 >> (4 * j)) & 0xFu;
+            }
+        }
+    } else if constexpr (ENC == BNPK_ENC_CODES) {
+        bad = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            codes |= bytes_2bit_to_byte(w[j] & 0x03030303u) << (8 * j);
+            const uint32_t hi = w[j] & 0xFCFCFCFCu;
+            const uint32_t nz = (((hi & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | hi) & 0x80808080u;
+            bad |= msb_to_nibble(nz) & (seq16 >> (4 * j)) & 0xFu;
+        }
+    } else {
+        bad = 0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const uint32_t code = s_lut[(w[b >> 2] >> (8 * (b & 3))) & 0xFFu];
+            codes |= (code & 3u) << (2 * b);
+            bad |= ((code >= 4u) ? 1u : 0u) & (seq16 >> b);
+        }
     }
-    __syncthreads();
-    total = s_warp[kTileWarps];
-    const uint32_t r = s_warp[warp] + inc - v;
-    __syncthreads();
-    return r;
+    return codes;
 }
 
 // -------------------------------------------------------------------------------------------
 // the tile kernel.  MODE 0 = split (write starts/lens), MODE 1 = fused count.
 // -------------------------------------------------------------------------------------------
+constexpr int kCtaThreads = (kTileBytes + kHaloBytes) / 64;      // one thread per 64 staged bytes
+constexpr int kCtaWarps = kCtaThreads / 32;
+constexpr int kMainThreads = kTileBytes / 64;
+constexpr int kNl0Bytes = (kCtaThreads + 4 + 15) & ~15;
+static_assert(kCtaThreads % 32 == 0 && kMainThreads % 32 == 0 && kCtaWarps <= 32, "tile geometry");
+
 template <int MODE, int ENC, bool SMEM_HIST, bool MINIMIZER>
-__global__ void __launch_bounds__(kTileThreads, MODE == 0 ? 2 : 1) tile_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_codes = smem;                                  // kStagedUnits + 4
-    uint32_t *s_flags = s_codes + kStagedUnits + 4;            // kStagedUnits
-    uint32_t *s_warp = s_flags + kStagedUnits;                 // kTileWarps + 1 (+pad to 32)
-    uint32_t *s_misc = s_warp + 32;                            // 16 words
-    uint16_t *s_rows = reinterpret_cast<uint16_t *>(s_misc + 16);                   // kRowCap
-    uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_rows + kRowCap);                 // 256
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_lut + 256);                   // n_bins (SMEM_HIST)
+    uint32_t *s_codes = smem;                                      // kStagedUnits + 4
+    uint32_t *s_row_end = s_codes + kStagedUnits + 4;              // kRowCap (tag << 16 | end)
+    uint16_t *s_row_start = reinterpret_cast<uint16_t *>(s_row_end + kRowCap);     // kRowCap
+    uint32_t *s_warp = reinterpret_cast<uint32_t *>(s_row_start + kRowCap);        // 32
+    uint32_t *s_misc = s_warp + 32;                                // 16
+    uint8_t *s_nl0 = reinterpret_cast<uint8_t *>(s_misc + 16);     // kNl0Bytes, '\r' mode only
+    uint8_t *s_lut = s_nl0 + kNl0Bytes;                            // 256
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_lut + 256);  // n_bins (SMEM_HIST)
     __shared__ int64_t s_line_base;
     __shared__ int64_t s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_halo = tid >= kMainThreads;
     uint64_t *tile_state = ws_tile_state(a.ws);
-    const bool cr = (MODE == 0 || a.field_line >= 0) && (a.status[BNPK_ST_CR] != 0);
+    const bool cr = a.status[BNPK_ST_CR] != 0;
 
     if (MODE == 1) {
         if (ENC == BNPK_ENC_LUT && tid < 256) s_lut[tid] = a.lut[tid];
         if (SMEM_HIST)
-            for (uint32_t b = tid; b < a.n_bins; b += kTileThreads) s_hist[b] = 0;
+            for (uint32_t b = tid; b < a.n_bins; b += kCtaThreads) s_hist[b] = 0;
+        if (tid < 4) s_codes[kStagedUnits + tid] = 0;
     }
-    if (tid < 4) s_codes[kStagedUnits + tid] = 0;
+    if (tid == 0) s_nl0[kCtaThreads] = 0;
+    // row-end slots carry a per-iteration tag; shared memory may hold a stale tagged value from an
+    // earlier launch, so start from zero (tag 0 is never used)
+    for (int i = tid; i < kRowCap; i += kCtaThreads) s_row_end[i] = 0;
     HistTarget ht;
     ht.global = a.hist;
     ht.smem = s_hist;
@@ -127,6 +191,11 @@ __global__ void __launch_bounds__(kTileThreads, MODE == 0 ? 2 : 1) tile_kernel(c
     ht.mask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
     ht.delta = 1ull;
     uint64_t acc_bases = 0, acc_values = 0;     // per-thread statistics, flushed once
+    // lines_per_entry is a power of two (2 or 4): phases and entry indices are masks and shifts
+    const uint32_t ls = (uint32_t)a.lpe_shift, pm = (1u << ls) - 1u;
+    const uint32_t fl = (uint32_t)a.field_line;
+    const uint32_t want = (fl - 1u) & pm;                          // phase of the newline before the field line
+    uint32_t iter = 0;
     __syncthreads();
 
     while (true) {
@@ -134,116 +203,122 @@ __global__ void __launch_bounds__(kTileThreads, MODE == 0 ? 2 : 1) tile_kernel(c
         __syncthreads();
         const int64_t tile = s_ticket;
         if (tile >= a.tile_end) break;
+        ++iter;
+        const uint32_t tag = (iter & 0xFFFFu) << 16;
         const size_t byte0 = (size_t)tile * kTileBytes;
         const int tile_len = (int)min((size_t)kTileBytes, a.n - byte0);
         const int staged_len = (MODE == 1) ? (int)min((size_t)(kTileBytes + kHaloBytes), a.n - byte0) : tile_len;
-        const int n_units = (staged_len + 15) >> 4;
+        const int my0 = tid * 64;                                   // first staged byte of this thread
 
-        // ---- stage: global -> registers -> (codes, flags) in shared memory -----------------
-        {
-            const bool aligned = ((reinterpret_cast<uintptr_t>(a.chunk) & 15) == 0);
-            constexpr int kMaxPer = (kStagedUnits + kTileThreads - 1) / kTileThreads;  // 5
-            uint4 q[kMaxPer];
-#pragma unroll
-            for (int j = 0; j < kMaxPer; ++j) {
-                const int u = tid + j * kTileThreads;
-                if (u < n_units) {
-                    if (aligned && (u + 1) * 16 <= staged_len)
-                        q[j] = ld_stream(reinterpret_cast<const uint4 *>(a.chunk + byte0) + u);
-                    else
-                        q[j] = load_unit_guarded(a.chunk, a.n, (int64_t)byte0 + (int64_t)u * 16);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kMaxPer; ++j) {
-                const int u = tid + j * kTileThreads;
-                if (u < kStagedUnits) {
-                    uint32_t c = 0, f = 0;
-                    if (u < n_units) {
-                        if (MODE == 1) encode_unit<ENC>(q[j], s_lut, c, f);
-                        else {
-                            f = bytes_lsb_to_nibble(__vcmpeq4(q[j].x, 0x0A0A0A0Au)) |
-                                (bytes_lsb_to_nibble(__vcmpeq4(q[j].y, 0x0A0A0A0Au)) << 4) |
-                                (bytes_lsb_to_nibble(__vcmpeq4(q[j].z, 0x0A0A0A0Au)) << 8) |
-                                (bytes_lsb_to_nibble(__vcmpeq4(q[j].w, 0x0A0A0A0Au)) << 12);
-                        }
-                        // bytes past the end of the data are neither newline nor valid
-                        const int over = (u + 1) * 16 - staged_len;
-                        if (over > 0) { const uint32_t keep = 0xFFFFu >> over; f &= keep | (keep << 16); }
-                    }
-                    s_codes[u] = c;
-                    s_flags[u] = f;
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- newline census of the tile proper (not the halo) -----------------------------
-        // thread t owns units [4t, 4t+4) = 64 bytes
+        // ---- 1. load my 64 bytes, newline mask ------------------------------------------------
+        uint32_t raw[16];
         uint64_t nlmask = 0;
-        {
-            const uint4 f4 = *reinterpret_cast<const uint4 *>(s_flags + 4 * tid);
-            nlmask = (uint64_t)(f4.x & 0xFFFFu) | ((uint64_t)(f4.y & 0xFFFFu) << 16) |
-                     ((uint64_t)(f4.z & 0xFFFFu) << 32) | ((uint64_t)(f4.w & 0xFFFFu) << 48);
-            const int first_byte = tid * 64;
-            if (first_byte >= tile_len) nlmask = 0;
-            else if (first_byte + 64 > tile_len) nlmask &= (~0ull) >> (64 - (tile_len - first_byte));
+        if (my0 < staged_len) {
+            const uint8_t *p = a.chunk + byte0 + my0;
+            if (my0 + 64 <= staged_len && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+                ld_stream_256(p, raw);
+                ld_stream_256(p + 32, raw + 8);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint4 q = load_unit_guarded(a.chunk, a.n, (int64_t)(byte0 + my0) + 16 * u);
+                    raw[4 * u] = q.x; raw[4 * u + 1] = q.y; raw[4 * u + 2] = q.z; raw[4 * u + 3] = q.w;
+                }
+            }
+            nlmask = eq_mask64(raw, 0x0A0A0A0Au);
+            if (my0 + 64 > staged_len) nlmask &= (~0ull) >> (64 - (staged_len - my0));
         }
-        uint32_t tile_nl;
-        const uint32_t my_excl = block_excl_scan((uint32_t)__popcll(nlmask), s_warp, tile_nl);
+        if (cr) s_nl0[tid] = (uint8_t)(nlmask & 1ull);
+
+        // ---- 2. block scan of newline counts (halo warp included), look-back over the tile proper
+        const uint32_t my_cnt = (uint32_t)__popcll(nlmask);
+        uint32_t inc = my_cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
         if (warp == 0) {
-            const uint64_t excl = lookback_exclusive(tile_state, tile, tile_nl, lane);
-            if (lane == 0) s_line_base = (int64_t)excl;
+            const uint32_t w = lane < kCtaWarps ? s_warp[lane] : 0;
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            if (lane < kCtaWarps) s_warp[lane] = winc - w;           // exclusive warp prefix
+            // newlines of the tile proper = everything before the halo warp(s)
+            const uint32_t tile_nl_w = __shfl_sync(0xffffffffu, winc, kMainThreads / 32 - 1);
+            const uint64_t excl = (a.debug & 1) ? (uint64_t)tile * 208ull : lookback_exclusive(tile_state, tile, tile_nl_w, lane);
+            if (lane == 0) {
+                s_line_base = (int64_t)excl;
+                s_misc[3] = tile_nl_w;
+                s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; s_misc[4] = 0xFFFFFFFFu;
+            }
         }
-        if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; }
         __syncthreads();
         const int64_t line_base = s_line_base;
-        const int lpe = a.lpe;
+        const uint32_t tile_nl = s_misc[3];
+        const uint32_t my_excl = s_warp[warp] + inc - my_cnt;       // tile-relative line index of my first byte
 
-        // rows whose field line starts in this tile: the newline j with (j+1) % lpe == field_line
-        // ends the previous line; the field line starts right after it.
-        const int64_t want = ((a.field_line - 1) % lpe + lpe) % lpe;   // j % lpe we look for
-        const int64_t j0 = line_base + (((want - line_base) % lpe) + lpe) % lpe;
-        const int64_t r_first = (j0 + 1) / lpe;
-        const int64_t n_rows_tile = (line_base + (int64_t)tile_nl - 1 >= j0)
-                                        ? (line_base + (int64_t)tile_nl - 1 - j0) / lpe + 1 : 0;
+        // 32-bit, tile-relative line arithmetic: global line = line_base + rel
+        const uint32_t base_phase = (uint32_t)line_base & pm;
+        const int64_t q0 = line_base >> ls;                          // entry index of the tile's first line
+        const uint32_t jr0 = (want - base_phase) & pm;               // first newline (rel) that precedes a field line
+        const uint32_t r_first_off = (base_phase + jr0 + 1u) >> ls;
+        const int64_t r_first = q0 + r_first_off;
+        const int n_rows_tile = (tile_nl > jr0) ? (int)(((tile_nl - 1u - jr0) >> ls) + 1u) : 0;
 
-        // ---- per-newline events ---------------------------------------------------------------
-        uint32_t my_complete = 0;   // tile-relative (p+1) of the last record-ending newline I own
-        auto newline_events = [&](int round) {
+        // ---- 3. one walk over my newlines: sequence-byte mask + row starts/ends + validation ----
+        uint64_t seqmask = 0;
+        uint32_t my_complete = 0;
+        auto walk = [&](const int round, const bool first_round) {
             uint64_t m = nlmask;
-            int64_t j = line_base + my_excl;
-            while (m) {
-                const int bit = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const int p = tid * 64 + bit;                      // tile-relative newline position
-                const size_t gp = byte0 + p;                       // global newline position
-                const int phase = (int)(j % lpe);
-                if (round == 0) {
-                    if (phase == lpe - 1) {
+            uint32_t rel = my_excl;                                  // rel line index of the current segment
+            int prev = 0;
+            const int slot_lo = round * kRowCap;
+            while (true) {
+                const int b = m ? (__ffsll((long long)m) - 1) : 64;
+                const uint32_t phase = (base_phase + rel) & pm;
+                if (MODE == 1 && first_round) {
+                    // bytes [prev, b) lie on line `rel`; rows owned by this tile have 1 <= rel <= tile_nl
+                    if (b > prev && phase == fl && rel - 1u < tile_nl)
+                        seqmask |= (b >= 64 ? ~0ull : ((1ull << b) - 1)) & ~((1ull << prev) - 1);
+                }
+                if (b >= 64) break;
+                // ---- the newline at bit b ends line `rel`
+                const int p = my0 + b;                               // tile-relative position
+                if (first_round && !is_halo && !(a.debug & 2)) {
+                    if (phase == pm) {                                // last line of an entry
                         my_complete = p + 1;
-                        // next entry's header char (one_line_buffer.py:155-173)
-                        if (gp + 1 < a.n && a.chunk[gp + 1] != a.header_char)
-                            atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], (long long)((j + 1) / lpe));
+                        const size_t gp = byte0 + p;
+                        if (gp + 1 < a.n && a.chunk[gp + 1] != a.header_char)      // one_line_buffer.py:155-173
+                            atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY],
+                                      (long long)(q0 + ((base_phase + rel + 1u) >> ls)));
                     }
-                    if (a.check_plus && phase == 1) {                 // fastq_buffer.py:38-45
+                    if (a.check_plus && phase == 1u) {                             // fastq_buffer.py:38-45
+                        const size_t gp = byte0 + p;
                         if (gp + 1 < a.n && a.chunk[gp + 1] != '+')
-                            atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY], (long long)(j / lpe));
+                            atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY],
+                                      (long long)(q0 + ((base_phase + rel) >> ls)));
                     }
                 }
                 if (MODE == 0) {
                     // split: start and end of the wanted line are published independently;
                     // lens[r] accumulates (end - start) mod 2^32 from two atomics.
+                    const size_t gp = byte0 + p;
                     if (phase == want) {
-                        const int64_t r = (j + 1) / lpe;
+                        const int64_t r = q0 + ((base_phase + rel + 1u) >> ls);
                         if ((size_t)r < a.max_rows) {
                             const int64_t s = (int64_t)gp + 1 + a.start_offset;
                             a.starts[r] = s;
                             atomicSub((unsigned int *)&a.lens[r], (unsigned int)(uint64_t)s);
                         }
                     }
-                    if (phase == a.field_line) {
-                        const int64_t r = j / lpe;
+                    if (phase == fl) {
+                        const int64_t r = q0 + ((base_phase + rel) >> ls);
                         if ((size_t)r < a.max_rows) {
                             int64_t e = (int64_t)gp;
                             if (cr && gp > 0 && a.chunk[gp - 1] == '\r') e -= 1;
@@ -251,73 +326,188 @@ __global__ void __launch_bounds__(kTileThreads, MODE == 0 ? 2 : 1) tile_kernel(c
                         }
                     }
                 } else {
-                    if (phase == want) {
-                        const int64_t slot = (j + 1) / lpe - r_first - (int64_t)round * kRowCap;
-                        if (slot >= 0 && slot < kRowCap) s_rows[slot] = (uint16_t)(p + 1 + a.start_offset);
+                    if (!is_halo && phase == want) {
+                        const int slot = (int)(((base_phase + rel + 1u) >> ls) - r_first_off) - slot_lo;
+                        if (slot >= 0 && slot < kRowCap) s_row_start[slot] = (uint16_t)(p + 1);
+                    }
+                    if (phase == fl) {
+                        const int slot_abs = (int)(((base_phase + rel) >> ls) - r_first_off);
+                        const int slot = slot_abs - slot_lo;
+                        if (slot_abs >= 0 && slot_abs < n_rows_tile && slot >= 0 && slot < kRowCap) {
+                            int e = p;
+                            if (cr && byte0 + p > 0 && a.chunk[byte0 + p - 1] == '\r') e -= 1;
+                            s_row_end[slot] = tag | (uint32_t)e;
+                        }
                     }
                 }
-                ++j;
+                if (b >= 63) break;
+                m &= m - 1;
+                prev = b + 1;
+                ++rel;
             }
         };
+        if (my0 < staged_len && !(a.debug & 4)) walk(0, true);
+        if (my_complete) atomicMax(&s_misc[0], my_complete);
 
-        if (MODE == 0) {
-            newline_events(0);
-            if (tile == 0 && tid == 0) {
-                if (a.n > 0 && a.chunk[0] != a.header_char)
-                    atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
-                if (a.field_line == 0 && a.max_rows > 0) {        // first line has no newline before it
-                    a.starts[0] = a.start_offset;
-                    atomicSub((unsigned int *)&a.lens[0], (unsigned int)a.start_offset);
-                }
+        if (MODE == 1) {
+            if (cr && seqmask) {
+                // a '\r' directly before the line's '\n' is not part of the row (one_line_buffer.py:175-182)
+                const uint64_t crmask = eq_mask64(raw, 0x0D0D0D0Du);
+                const uint64_t next_nl = (nlmask >> 1) | ((uint64_t)s_nl0[tid + 1] << 63);
+                seqmask &= ~(crmask & next_nl);
             }
-            if (my_complete) atomicMax(&s_misc[0], my_complete);
-            __syncthreads();
-        } else {
-            if (tile == 0 && tid == 0 && a.n > 0 && a.chunk[0] != a.header_char)
-                atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
-            const int n_rounds = (int)((n_rows_tile + kRowCap - 1) / kRowCap);
-            for (int round = 0; round < (n_rounds > 0 ? n_rounds : 1); ++round) {
-                newline_events(round);
-                if (round == 0 && my_complete) atomicMax(&s_misc[0], my_complete);
-                __syncthreads();
-                const int rows_here = (int)min((int64_t)kRowCap, n_rows_tile - (int64_t)round * kRowCap);
-                for (int slot = warp; slot < rows_here; slot += kTileWarps) {
-                    const int b0 = s_rows[slot];
-                    const int64_t r = r_first + (int64_t)round * kRowCap + slot;
-                    if (b0 > staged_len) continue;                  // start_offset ran past the data
-                    const int e = find_newline(s_flags, b0, staged_len, lane);
-                    if (e < 0) {
-                        if (byte0 + staged_len >= a.n) continue;    // unterminated last line: not an entry
-                        if (lane == 0) {                            // long row: defer
-                            const unsigned long long d = atomicAdd((unsigned long long *)(a.ws + kWsDeferred), 1ull);
-                            if (d < a.deferred_cap) {
-                                uint64_t *def = ws_deferred(a.ws, a.n_tiles_total);
-                                def[2 * d] = byte0 + b0;
-                                def[2 * d + 1] = (uint64_t)r;
-                            }
-                        }
-                        continue;
-                    }
-                    int L = e - b0;
-                    if (cr && L > 0 && a.chunk[byte0 + e - 1] == '\r') L -= 1;
-                    const int bad = find_invalid(s_flags, b0, b0 + L, lane);
-                    if (bad >= 0) {
-                        if (lane == 0)
-                            atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE], (long long)((r << 32) | (int64_t)(bad - b0)));
-                        continue;
-                    }
-                    if (lane == 0) {
-                        acc_bases += (uint64_t)L;
-                        atomicMax(&s_misc[1], (uint32_t)b0 + 1u);
-                        atomicMax(&s_misc[2], (uint32_t)(r - r_first) + 1u);
-                    }
-                    const int span = MINIMIZER ? a.window : a.k;
-                    if (L >= span) acc_values += row_count<SMEM_HIST, MINIMIZER>(s_codes, b0, L, a.k, a.window, ht, lane);
+            if (my0 + 64 > staged_len) seqmask = (my0 < staged_len) ? (seqmask & ((~0ull) >> (64 - (staged_len - my0)))) : 0;
+            // ---- 4. encode + validate only the units that hold sequence bytes -------------------
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t seq16 = (uint32_t)(seqmask >> (16 * u)) & 0xFFFFu;
+                if (seq16 && !(a.debug & 16)) {
+                    uint32_t bad;
+                    s_codes[tid * 4 + u] = encode_unit_seq<ENC>(raw + 4 * u, seq16, s_lut, bad);
+                    if (bad) atomicMin(&s_misc[4], (uint32_t)(my0 + 16 * u));   // rare: resolved after the tile
                 }
-                __syncthreads();
             }
         }
-        // ---- per-tile global bookkeeping (one atomic each) --------------------------------------
+        if (tile == 0 && tid == 0) {
+            if (a.n > 0 && a.chunk[0] != a.header_char)
+                atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
+            if (MODE == 0 && fl == 0 && a.max_rows > 0) {           // the first line has no newline before it
+                a.starts[0] = a.start_offset;
+                atomicSub((unsigned int *)&a.lens[0], (unsigned int)a.start_offset);
+            }
+        }
+        __syncthreads();
+
+        // ---- 5. rows -> histogram ----------------------------------------------------------------
+        if (MODE == 1) {
+            auto defer_row = [&](uint64_t start, uint64_t r) {
+                const unsigned long long d = atomicAdd((unsigned long long *)(a.ws + kWsDeferred), 1ull);
+                if (d < a.deferred_cap) {
+                    uint64_t *def = ws_deferred(a.ws, a.n_tiles_total);
+                    def[2 * d] = start;
+                    def[2 * d + 1] = r;
+                } else {
+                    a.status[BNPK_ST_OVERFLOW] = 1;
+                }
+            };
+            const int n_rounds = (n_rows_tile + kRowCap - 1) / kRowCap;
+            for (int round = 0; round < (n_rounds > 0 ? n_rounds : 1); ++round) {
+                if (round > 0) {
+                    // more rows than the shared row list holds (lines of ~30 bytes or less): redo the walk
+                    // for the next window of slots
+                    __syncthreads();
+                    if (my0 < staged_len) walk(round, false);
+                    __syncthreads();
+                }
+                const int slot_lo = round * kRowCap;
+                const int rows_here = min(kRowCap, n_rows_tile - slot_lo);
+                auto row_bounds = [&](int slot, int &b0, int &L) -> bool {
+                    b0 = s_row_start[slot];
+                    const uint32_t ew = s_row_end[slot];
+                    if ((ew & 0xFFFF0000u) != tag) {                // no terminating newline in the staged region
+                        if (byte0 + staged_len < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + slot_lo + slot));   // long row
+                        return false;                               // (else: unterminated last line, not an entry)
+                    }
+                    L = (int)(ew & 0xFFFFu) - b0;
+                    return true;
+                };
+                if (a.debug & 8) {
+                } else if constexpr (!MINIMIZER) {
+                    const int sub = tid & 3, grp = tid >> 2;
+                    const uint64_t kmask = (1ull << (2 * a.k)) - 1;
+                    const bool fast = ht.mask && ht.mask <= 0xFFFFFFFFull;
+                    const uint32_t m32 = (uint32_t)(ht.mask & kmask);
+                    for (int slot0 = 0; slot0 < rows_here; slot0 += kCtaThreads / 4) {
+                        const int slot = slot0 + grp;
+                        int b0 = 0, L = 0;
+                        bool ok = false;
+                        if (sub == 0 && slot < rows_here) ok = row_bounds(slot, b0, L);
+                        ok = __shfl_sync(0xffffffffu, ok, lane & ~3);
+                        b0 = __shfl_sync(0xffffffffu, b0, lane & ~3);
+                        L = __shfl_sync(0xffffffffu, L, lane & ~3);
+                        if (!ok) continue;
+                        if (sub == 0) {
+                            acc_bases += (uint64_t)L;
+                            atomicMax(&s_misc[1], (uint32_t)b0 + 1u);
+                            atomicMax(&s_misc[2], (uint32_t)(slot_lo + slot) + 1u);
+                        }
+                        const int npos = L - a.k + 1;
+                        for (int p0 = sub * 32; p0 < npos; p0 += 128) {
+                            const int n_here = min(32, npos - p0);
+                            acc_values += (uint64_t)n_here;
+                            if (fast) {
+                                const uint32_t bit = 2u * (uint32_t)(b0 + p0);
+                                const uint32_t idx = bit >> 5, sh = bit & 31u;
+                                const uint32_t w0 = s_codes[idx], w1 = s_codes[idx + 1], w2 = s_codes[idx + 2], w3 = s_codes[idx + 3];
+                                const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32;
+                                    if (j < n_here) {
+                                        if constexpr (SMEM_HIST) atomicAdd(s_hist + v, 1u);
+                                        else atomicAdd(a.hist + v, 1ull);
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32;
+                                    if (j + 16 < n_here) {
+                                        if constexpr (SMEM_HIST) atomicAdd(s_hist + v, 1u);
+                                        else atomicAdd(a.hist + v, 1ull);
+                                    }
+                                }
+                            } else {
+                                for (int j = 0; j < n_here; ++j)
+                                    hist_add<SMEM_HIST>(ht, stream_64(s_codes, (uint32_t)(b0 + p0 + j)) & kmask);
+                            }
+                        }
+                    }
+                } else {
+                    for (int slot = warp; slot < rows_here; slot += kCtaWarps) {
+                        int b0 = 0, L = 0;
+                        bool ok = false;
+                        if (lane == 0) ok = row_bounds(slot, b0, L);
+                        ok = __shfl_sync(0xffffffffu, ok, 0);
+                        b0 = __shfl_sync(0xffffffffu, b0, 0);
+                        L = __shfl_sync(0xffffffffu, L, 0);
+                        if (!ok) continue;
+                        if (lane == 0) {
+                            acc_bases += (uint64_t)L;
+                            atomicMax(&s_misc[1], (uint32_t)b0 + 1u);
+                            atomicMax(&s_misc[2], (uint32_t)(slot_lo + slot) + 1u);
+                        }
+                        if (L >= a.window) acc_values += row_count<SMEM_HIST, true>(s_codes, b0, L, a.k, a.window, ht, lane);
+                    }
+                }
+                // an invalid base was seen: find its (row, position) -- error path only
+                if (s_misc[4] != 0xFFFFFFFFu) {
+                    __syncthreads();
+                    if (warp == 0) {
+                        const int unit0 = (int)s_misc[4];
+                        for (int slot = lane; slot < rows_here; slot += 32) {
+                            const uint32_t ew = s_row_end[slot];
+                            if ((ew & 0xFFFF0000u) != tag) continue;
+                            const int b0 = s_row_start[slot], e = (int)(ew & 0xFFFFu);
+                            if (e <= unit0 || b0 >= unit0 + 16) continue;
+                            for (int p = max(b0, unit0); p < min(e, unit0 + 16); ++p) {
+                                const uint32_t c = a.chunk[byte0 + p];
+                                bool okb;
+                                if (ENC == BNPK_ENC_CODES) okb = c < 4;
+                                else if (ENC == BNPK_ENC_LUT) okb = s_lut[c] < 4;
+                                else { const uint32_t u = c | 0x20u; okb = (u == 'a' || u == 'c' || u == 'g' || u == 't'); }
+                                if (!okb) {
+                                    atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE],
+                                              (long long)(((r_first + slot_lo + slot) << 32) | (int64_t)(p - b0)));
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- 6. per-tile global bookkeeping (one atomic each) -----------------------------------
         if (tid == 0) {
             if (s_misc[0]) atomicMax((unsigned long long *)&a.status[BNPK_ST_N_COMPLETE_BYTES], (unsigned long long)(byte0 + s_misc[0]));
             if (MODE == 1 && s_misc[1]) {
@@ -326,14 +516,14 @@ __global__ void __launch_bounds__(kTileThreads, MODE == 0 ? 2 : 1) tile_kernel(c
             }
             if (tile == a.n_tiles_total - 1) a.status[BNPK_ST_N_LINES] = line_base + tile_nl;
         }
-        __syncthreads();
+        if (MODE == 0) __syncthreads();
     }
 
     // ---- flush ---------------------------------------------------------------------------------
     if (MODE == 1) {
         if (SMEM_HIST) {
             __syncthreads();
-            for (uint32_t b = tid; b < a.n_bins; b += kTileThreads) {
+            for (uint32_t b = tid; b < a.n_bins; b += kCtaThreads) {
                 const uint32_t c = s_hist[b];
                 if (c) atomicAdd(a.hist + b, (unsigned long long)c);
             }
@@ -353,14 +543,16 @@ __global__ void finalize_status_kernel(int64_t *status, int lpe) {
 }
 
 static size_t tile_smem_bytes(int mode, uint64_t n_bins, bool smem_hist) {
-    size_t words = (kStagedUnits + 4) + kStagedUnits + 32 + 16;
-    size_t bytes = words * 4 + kRowCap * 2 + 256;
+    size_t bytes = (size_t)(kStagedUnits + 4) * 4 + (size_t)kRowCap * 4 + (size_t)kRowCap * 2 + 32 * 4 + 16 * 4 +
+                   kNl0Bytes + 256;
     if (mode == 1 && smem_hist) bytes += n_bins * 4;
     return bytes;
 }
 
 template <int MODE, int ENC, bool SMEM_HIST, bool MINIMIZER>
-static int launch_tile(const TileArgs &a, cudaStream_t st) {
+static int launch_tile(const TileArgs &a_in, cudaStream_t st) {
+    TileArgs a = a_in;
+    { const char *d = getenv("BNPK_DEBUG"); a.debug = d ? atoi(d) : 0; }
     auto kern = tile_kernel<MODE, ENC, SMEM_HIST, MINIMIZER>;
     const size_t smem = tile_smem_bytes(MODE, a.n_bins, SMEM_HIST);
     static thread_local bool attr_done = false;  // per instantiation
@@ -369,13 +561,13 @@ static int launch_tile(const TileArgs &a, cudaStream_t st) {
         attr_done = true;
     }
     int per_sm = 1;
-    BNPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
+    BNPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCtaThreads, smem));
     if (per_sm < 1) return set_err(BNPK_E_BINS, "tile kernel does not fit shared memory");
     const int64_t n_tiles = a.tile_end - a.tile_begin;
     if (n_tiles <= 0) return 0;
     const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)sm_count() * per_sm);
     profile_before(st);
-    kern<<<(unsigned)grid, kTileThreads, smem, st>>>(a);
+    kern<<<(unsigned)grid, kCtaThreads, smem, st>>>(a);
     profile_after(st);
     BNPK_LAUNCHED("tile_kernel");
     return 0;
@@ -398,10 +590,11 @@ static int launch_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStr
     return set_err(BNPK_E_BADARG, "bad enc_mode");
 }
 
+static size_t deferred_capacity(size_t n) { return n / kHaloBytes + n / 1024 + 16; }
+
 size_t tile_workspace_bytes(size_t n) {
     const size_t n_tiles = (n + kTileBytes - 1) / kTileBytes + 1;
-    const size_t deferred = n / kHaloBytes + 16;
-    return (kWsHeaderWords + n_tiles + 2 * deferred) * sizeof(uint64_t);
+    return (kWsHeaderWords + n_tiles + 2 * deferred_capacity(n)) * sizeof(uint64_t);
 }
 
 bool use_smem_hist(int64_t n_bins, int hist_mode) {
@@ -415,10 +608,12 @@ int chunk_kmer_count_impl(const uint8_t *chunk, size_t n, size_t slice_begin, si
                           int64_t *status, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     if (k < 1 || k > 31) return set_err(BNPK_E_K, "k must be larger than 0 and smaller than 32");
     if (window != 0 && window < k) return set_err(BNPK_E_WINDOW, "kmer size must be smaller than window size");
+    if (window > 1024) return set_err(BNPK_E_WINDOW, "window_size above 1024 is not supported");
     if (n_bins < 1) return set_err(BNPK_E_BINS, "n_bins must be positive");
     if (hist_mode == BNPK_HIST_SMEM && n_bins > kSmemMaxBins) return set_err(BNPK_E_BINS, "too many bins for the shared-memory histogram");
     if (enc_mode == BNPK_ENC_LUT && !lut256) return set_err(BNPK_E_BADARG, "lut256 required");
-    if (lpe < 2 || slice_end > n || slice_begin > slice_end) return set_err(BNPK_E_BADARG, "bad slice");
+    if ((lpe != 2 && lpe != 4) || slice_end > n || slice_begin > slice_end)
+        return set_err(BNPK_E_BADARG, "lines_per_entry must be 2 or 4; slice must lie inside the chunk");
     if (workspace_bytes < tile_workspace_bytes(n)) return set_err(BNPK_E_WORKSPACE, "workspace too small");
     if (n == 0) return 0;
     const int64_t n_tiles_total = (int64_t)((n + kTileBytes - 1) / kTileBytes);
@@ -432,9 +627,9 @@ int chunk_kmer_count_impl(const uint8_t *chunk, size_t n, size_t slice_begin, si
     a.chunk = chunk; a.n = n;
     a.tile_begin = tiles_done_at(slice_begin);
     a.tile_end = final_slice ? n_tiles_total : tiles_done_at(slice_end);
-    a.lpe = lpe; a.field_line = 1; a.start_offset = 0; a.header_char = header_char; a.check_plus = check_plus;
-    a.trim_cr = trim_cr; a.status = status; a.ws = (uint64_t *)workspace; a.n_tiles_total = n_tiles_total;
-    a.deferred_cap = n / kHaloBytes + 16;
+    a.lpe = lpe; a.lpe_shift = lpe == 4 ? 2 : 1; a.field_line = 1; a.start_offset = 0; a.header_char = header_char;
+    a.check_plus = check_plus; a.status = status; a.ws = (uint64_t *)workspace; a.n_tiles_total = n_tiles_total;
+    a.deferred_cap = deferred_capacity(n);
     a.lut = lut256; a.k = k; a.window = window; a.n_bins = (uint64_t)n_bins; a.hist = (unsigned long long *)hist;
     if (slice_begin == 0) {
         BNPK_CUDA(cudaMemsetAsync(workspace, 0, (kWsHeaderWords + n_tiles_total + 1) * sizeof(uint64_t), st));
@@ -458,21 +653,21 @@ int chunk_kmer_count_impl(const uint8_t *chunk, size_t n, size_t slice_begin, si
 int line_split_impl(const uint8_t *chunk, size_t n, int lpe, int field_line, int start_offset, uint8_t header_char,
                     int check_plus, int trim_cr, int64_t *starts, int32_t *lens, size_t max_rows, int64_t *status,
                     void *workspace, size_t workspace_bytes, cudaStream_t st) {
-    if (lpe < 1 || field_line < 0 || field_line >= lpe) return set_err(BNPK_E_BADARG, "bad line layout");
+    if ((lpe != 1 && lpe != 2 && lpe != 4) || field_line < 0 || field_line >= lpe)
+        return set_err(BNPK_E_BADARG, "lines_per_entry must be 1, 2 or 4 and 0 <= field_line < lines_per_entry");
     if (workspace_bytes < tile_workspace_bytes(n)) return set_err(BNPK_E_WORKSPACE, "workspace too small");
     if (n == 0) return 0;
     TileArgs a{};
     a.chunk = chunk; a.n = n;
     a.n_tiles_total = (int64_t)((n + kTileBytes - 1) / kTileBytes);
     a.tile_begin = 0; a.tile_end = a.n_tiles_total;
-    a.lpe = lpe; a.field_line = field_line; a.start_offset = start_offset; a.header_char = header_char;
-    a.check_plus = check_plus; a.trim_cr = trim_cr; a.status = status; a.ws = (uint64_t *)workspace;
+    a.lpe = lpe; a.lpe_shift = lpe == 4 ? 2 : (lpe == 2 ? 1 : 0); a.field_line = field_line; a.start_offset = start_offset;
+    a.header_char = header_char; a.check_plus = check_plus; a.status = status; a.ws = (uint64_t *)workspace;
     a.starts = starts; a.lens = lens; a.max_rows = max_rows; a.n_bins = 1;
     if (max_rows) BNPK_CUDA(cudaMemsetAsync(lens, 0, max_rows * sizeof(int32_t), st));
     BNPK_CUDA(cudaMemsetAsync(workspace, 0, (kWsHeaderWords + a.n_tiles_total + 1) * sizeof(uint64_t), st));
     cr_detect_kernel<<<1, 32, 0, st>>>(chunk, n, lpe, trim_cr, status);
     BNPK_LAUNCHED("cr_detect_kernel");
-    BNPK_CUDA(cudaMemsetAsync(a.ws + kWsTicket, 0, sizeof(uint64_t), st));
     int rc = launch_tile<0, BNPK_ENC_ASCII_ACGT, false, false>(a, st);
     if (rc) return rc;
     finalize_status_kernel<<<1, 32, 0, st>>>(status, lpe);

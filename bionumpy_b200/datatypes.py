@@ -24,6 +24,8 @@ class _Entries:
     def __len__(self):
         if self._buffer is not None:
             return self._buffer.count_entries()
+        if not self._values:
+            return 0
         return len(next(iter(self._values.values())))
 
     def __repr__(self):

@@ -131,7 +131,15 @@ class CudaOneLineBuffer:
     def fused_kmer_histogram(self, k, window_size, n_bins, enc_mode, lut):
         hist, status = ops.chunk_kmer_count(self._data, k, n_bins, None, window_size, self.n_lines_per_entry,
                                             ord(self.HEADER), False, 1 if self._cr else 0, enc_mode, lut)
-        bad = ops.read_status(status).bad_base(self._n_records)
+        st = ops.read_status(status)
+        if st.overflow:
+            # pathological line structure (more odd rows than the fused pass keeps scratch for):
+            # take the general two-kernel route over the row-offset vector instead
+            seq = self.get_field_by_number(1)
+            hist, status = ops.rows_kmer_count(seq._data, seq._starts.contiguous(), seq._lens.contiguous(), enc_mode,
+                                               k, n_bins, window_size, lut)
+            st = ops.read_status(status)
+        bad = st.bad_base(self._n_records)
         if bad is not None:
             from ..encodings.alphabet_encoding import DNAEncoding
             DNAEncoding._raise_encoding_error(bad[0], bad[1], self.get_field_by_number(1)._lens)

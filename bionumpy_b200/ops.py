@@ -29,6 +29,7 @@ class ScanStatus:
     n_values = property(lambda s: s.words[nv.ST_N_VALUES])
     n_long_rows = property(lambda s: s.words[nv.ST_N_LONG_ROWS])
     cr = property(lambda s: bool(s.words[nv.ST_CR]))
+    overflow = property(lambda s: bool(s.words[nv.ST_OVERFLOW]))
 
     @property
     def bad_header_entry(self):
