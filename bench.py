@@ -210,6 +210,7 @@ def main():
 
     def step():
         hist.zero_()
+        nv.check(lib.bnpk_status_init(nv.ptr(status), nv.stream_ptr()))
         ops.chunk_kmer_count(chunk, args.k, args.buckets, hist=hist, window_size=args.window, status=status)
         all_reduce_histogram(hist)
 
