@@ -56,31 +56,40 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 # CPU baseline = the oracle's NumPy port of the reference path (test infrastructure; timed, not shipped)
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(job):
-    first, n, k, buckets, window = job
-    import numpy as np
+_CPU_CHUNK = None
+
+
+def _cpu_init(chunk_reads):
+    """Every worker builds one ~4.8 MB synthetic chunk once (not timed)."""
+    global _CPU_CHUNK
     from oracle import bnp_oracle as oracle
-    chunk = oracle.synthetic_fastq(first, n)
+    _CPU_CHUNK = oracle.synthetic_fastq((os.getpid() % 1000) * chunk_reads, chunk_reads)
+
+
+def _cpu_worker(job):
+    k, buckets, window = job
+    from oracle import bnp_oracle as oracle
     t0 = time.perf_counter()
-    hist, size, n_bases = oracle.fastq_chunk_kmer_counts(chunk, k, buckets, True, window_size=window)
+    hist, size, n_bases = oracle.fastq_chunk_kmer_counts(_CPU_CHUNK, k, buckets, True, window_size=window)
     return time.perf_counter() - t0, n_bases, int(hist.sum())
 
 
 def cpu_baseline(k, buckets, window, sample_reads, n_procs):
-    """Reference op sequence on `n_procs` processes, each over disjoint 5 MB-ish chunks
-    (bionumpy's default min_chunk_size, io/parser.py:96); input generation is not timed."""
-    chunk_reads = 15_000                                  # ~4.8 MB, the reference's default chunk size
-    jobs = [(i * chunk_reads, chunk_reads, k, buckets, window) for i in range(max(1, sample_reads // chunk_reads))]
-    t0 = time.perf_counter()
+    """The reference op sequence (oracle port) on `n_procs` processes, each over ~4.8 MB chunks (bionumpy's default
+    min_chunk_size, io/parser.py:96), input already in RAM.  Returns (Gbases/s, bases, wall seconds)."""
+    chunk_reads = 15_000
+    n_jobs = max(n_procs, sample_reads // chunk_reads)
+    jobs = [(k, buckets, window)] * n_jobs
     if n_procs == 1:
+        _cpu_init(chunk_reads)
+        _cpu_worker(jobs[0])
         res = [_cpu_worker(j) for j in jobs]
-        busy = sum(r[0] for r in res)
-        wall = busy
+        wall = sum(r[0] for r in res)
     else:
-        with mp.get_context("fork").Pool(n_procs) as pool:
-            pool.map(_cpu_worker, jobs[:n_procs])          # warm the workers (imports)
+        with mp.get_context("fork").Pool(n_procs, initializer=_cpu_init, initargs=(chunk_reads,)) as pool:
+            pool.map(_cpu_worker, jobs[:n_procs], chunksize=1)          # warm up (imports, page faults)
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, jobs)
+            res = pool.map(_cpu_worker, jobs, chunksize=1)
             wall = time.perf_counter() - t0
     bases = sum(r[1] for r in res)
     return bases / wall / 1e9, bases, wall
@@ -157,7 +166,7 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     vals = []
-    sample = args.cpu_sample_reads
+    sample = max(args.cpu_sample_reads, 15_000 * cores * 2)      # at least two ~4.8 MB chunks per core and step
     for i in range(args.warmup + args.steps):
         v, bases, wall = cpu_baseline(args.k, args.buckets, args.window, sample, cores)
         if i >= args.warmup:
@@ -353,11 +362,12 @@ def main():
     # ---- CPU baseline: the reference path's NumPy port on this box's host cores (rank 0, N = 1) -------
     if rank == 0 and world == 1:
         cores = os.cpu_count() or 1
-        v1, bases1, wall1 = cpu_baseline(args.k, args.buckets, args.window, min(args.cpu_sample_reads, 60_000), 1)
-        vN, basesN, wallN = cpu_baseline(args.k, args.buckets, args.window, args.cpu_sample_reads * 4, cores)
+        v1, bases1, wall1 = cpu_baseline(args.k, args.buckets, args.window, 60_000, 1)
+        n_sample = 15_000 * cores * 6                         # six ~4.8 MB chunks per core
+        vN, basesN, wallN = cpu_baseline(args.k, args.buckets, args.window, n_sample, cores)
         line["cpu_baseline"] = {"value": round(vN, 4), "unit": "Gbases/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_sample_reads * 4} synthetic reads in ~4.8 MB chunks, one process per core "
-                                          f"({wallN:.1f} s); single core: {v1:.4f} Gbases/s on {min(args.cpu_sample_reads, 60_000)} reads",
+                                "sample": f"{n_sample} synthetic reads = {basesN / 1e9:.2f} Gbases in ~4.8 MB chunks, one process "
+                                          f"per core, {wallN:.1f} s wall; single core: {v1:.4f} Gbases/s on 60000 reads",
                                 "single_core_value": round(v1, 4)}
     if rank == 0:
         print(json.dumps(line), flush=True)
