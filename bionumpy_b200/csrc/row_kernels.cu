@@ -39,34 +39,6 @@ struct RowArgs {
     int lpe;
 };
 
-// length of the line starting at global byte `start` (distance to the next '\n'); -1 if the data
-// ends first.  Warp-wide.
-__device__ int64_t warp_line_len(const uint8_t *base, size_t n, int64_t start, int lane) {
-    const int off = (int)((reinterpret_cast<uintptr_t>(base) + start) & 15);
-    int64_t u0 = start - off;
-    bool first = true;
-    while (u0 < (int64_t)n) {
-        const int64_t ub = u0 + 16 * (int64_t)lane;
-        uint32_t m = 0;
-        if (ub < (int64_t)n) {
-            const uint4 q = load_unit_guarded(base, n, ub);
-            m = bytes_lsb_to_nibble(__vcmpeq4(q.x, 0x0A0A0A0Au)) | (bytes_lsb_to_nibble(__vcmpeq4(q.y, 0x0A0A0A0Au)) << 4) |
-                (bytes_lsb_to_nibble(__vcmpeq4(q.z, 0x0A0A0A0Au)) << 8) | (bytes_lsb_to_nibble(__vcmpeq4(q.w, 0x0A0A0A0Au)) << 12);
-            if (first && lane == 0) m &= 0xFFFFu << off;
-            // guarded loads read 0 past the end, never '\n'
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, m != 0);
-        if (b) {
-            const int src = __ffs(b) - 1;
-            const int64_t pos = ub + __ffs(m) - 1;
-            return __shfl_sync(0xffffffffu, pos, src) - start;
-        }
-        first = false;
-        u0 += 512;
-    }
-    return -1;
-}
-
 template <int RM, int ENC, bool SMEM_HIST>
 __device__ void warp_row(const RowArgs &a, uint32_t *w_codes, uint32_t *w_flags, const uint8_t *s_lut,
                          const HistTarget &ht, int64_t start, int64_t L, int64_t r, int64_t out_off, int lane,

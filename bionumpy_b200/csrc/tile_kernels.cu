@@ -27,6 +27,7 @@ struct TileArgs {
     int64_t *status;
     uint64_t *ws;                  // header | tile_state[] | deferred[]
     int64_t n_tiles_total;
+    uint64_t *deferred;            // long-row list (start, entry) pairs
     size_t deferred_cap;
     // split
     int64_t *starts;
@@ -40,10 +41,6 @@ struct TileArgs {
     unsigned long long *hist;
 };
 
-__device__ __forceinline__ uint64_t *ws_tile_state(uint64_t *ws) { return ws + kWsHeaderWords; }
-__device__ __forceinline__ uint64_t *ws_deferred(uint64_t *ws, int64_t n_tiles_total) {
-    return ws + kWsHeaderWords + n_tiles_total;
-}
 
 // -------------------------------------------------------------------------------------------
 // init: decide '\r' trimming like OneLineBuffer._modify_for_carriage_return
@@ -51,22 +48,20 @@ __device__ __forceinline__ uint64_t *ws_deferred(uint64_t *ws, int64_t n_tiles_t
 // `lines_per_entry` entries ends in '\r'.
 // -------------------------------------------------------------------------------------------
 __global__ void cr_detect_kernel(const uint8_t *chunk, size_t n, int lpe, int trim_cr, int64_t *status) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     int64_t cr = 0;
     if (trim_cr == 1) cr = 1;
     if (trim_cr < 0) {
-        size_t p = 0;
-        int line = 0;
-        const int max_lines = lpe * lpe;
-        const size_t limit = n < (size_t)(8u << 20) ? n : (size_t)(8u << 20);
-        for (; p < limit && line < max_lines; ++p) {
-            if (chunk[p] == '\n') {
-                if (line % lpe == 0 && p > 0 && chunk[p - 1] == '\r') { cr = 1; break; }
-                ++line;
-            }
+        int64_t pos = 0;
+        for (int line = 0; line < lpe * lpe && pos < (int64_t)n; ++line) {
+            const int64_t len = warp_line_len(chunk, n, pos, lane);
+            if (len < 0) break;
+            if (line % lpe == 0 && len > 0 && chunk[pos + len - 1] == '\r') { cr = 1; break; }
+            pos += len + 1;
         }
     }
-    status[BNPK_ST_CR] = cr;
+    if (lane == 0) status[BNPK_ST_CR] = cr;
 }
 
 // 256-bit streaming load (sm_100: LDG.E.256), read-only path, no L1 allocation
@@ -155,6 +150,86 @@ constexpr int kMainThreads = kTileBytes / 64;
 constexpr int kNl0Bytes = (kCtaThreads + 4 + 15) & ~15;
 static_assert(kCtaThreads % 32 == 0 && kMainThreads % 32 == 0 && kCtaWarps <= 32, "tile geometry");
 
+// ---- two-level look-back state in the workspace ------------------------------------------------
+//   tile_state[t]  : flag|value, AGG = newlines of tile t, PREFIX = newlines of tiles 0..t
+//   block_cnt[b]   : atomic (count << 56 | sum) over the 32 tiles of block b
+//   block_state[b] : flag|value, AGG = newlines of the whole block, PREFIX = newlines of tiles 0..32b+31
+// A tile resolves its exclusive prefix from <= 31 tile entries of its own block plus <= 32 block
+// entries: two loads per lane, issued one pipeline stage before they are needed.
+struct LookbackArrays {
+    uint64_t *tile_state, *block_cnt, *block_state;
+};
+__device__ __forceinline__ LookbackArrays lookback_arrays(uint64_t *ws, int64_t n_tiles_total) {
+    LookbackArrays l;
+    l.tile_state = ws + kWsHeaderWords;
+    const int64_t nb = (n_tiles_total >> 5) + 2;
+    l.block_cnt = l.tile_state + n_tiles_total + 1;
+    l.block_state = l.block_cnt + nb;
+    return l;
+}
+__device__ __forceinline__ void lookback_publish(const LookbackArrays &l, int64_t tile, uint64_t agg) {
+    st_relaxed(l.tile_state + tile, (tile == 0 ? kFlagPrefix : kFlagAgg) | agg);
+    const int64_t b = tile >> 5;
+    const unsigned long long old = atomicAdd((unsigned long long *)(l.block_cnt + b), (1ull << 56) | agg);
+    if ((old >> 56) == 31ull)
+        atomicMax((unsigned long long *)(l.block_state + b), kFlagAgg | ((old & ((1ull << 56) - 1)) + agg));
+}
+__device__ __forceinline__ void lookback_issue(const LookbackArrays &l, int64_t tile, int lane, uint64_t &lbA, uint64_t &lbB) {
+    const int i = (int)(tile & 31);
+    const int64_t b = tile >> 5;
+    lbA = (lane < i) ? ld_relaxed(l.tile_state + tile - 1 - lane) : kFlagPrefix;
+    lbB = (b - 1 - lane >= 0) ? ld_relaxed(l.block_state + (b - 1 - lane)) : kFlagPrefix;
+}
+// Warp-wide.  Returns the exclusive prefix of `tile` and publishes its inclusive prefix.
+__device__ __forceinline__ uint64_t lookback_finish(const LookbackArrays &l, int64_t tile, uint64_t agg, int lane,
+                                                    uint64_t lbA, uint64_t lbB) {
+    const int i = (int)(tile & 31);
+    int64_t b = tile >> 5;
+    uint64_t excl = 0;
+    bool have = false;
+    // ---- my own block: tiles 32b .. tile-1 (lane 0 = tile-1)
+    while (true) {
+        const bool valid = lane < i;
+        const unsigned pref = __ballot_sync(0xffffffffu, valid && (lbA >> 62) == 2);
+        const unsigned zero = __ballot_sync(0xffffffffu, valid && (lbA >> 62) == 0);
+        const unsigned upto = pref ? ((pref & (0u - pref)) << 1) - 1u : 0xffffffffu;     // lanes 0..first prefix
+        if (zero & upto) {                                   // a needed predecessor has not published yet
+            if (valid) lbA = ld_relaxed(l.tile_state + tile - 1 - lane);
+            continue;
+        }
+        const uint64_t v = (valid && ((1u << lane) & upto)) ? (lbA & kValueMask) : 0;
+        excl = warp_sum_u64(v);
+        have = pref != 0;
+        break;
+    }
+    // ---- whole blocks before mine (lane 0 = block b-1)
+    int64_t bb = b;
+    while (!have) {
+        const unsigned pref = __ballot_sync(0xffffffffu, (lbB >> 62) == 2);
+        const unsigned zero = __ballot_sync(0xffffffffu, (lbB >> 62) == 0);
+        const unsigned upto = pref ? ((pref & (0u - pref)) << 1) - 1u : 0xffffffffu;
+        if (zero & upto) {
+            lbB = (bb - 1 - lane >= 0) ? ld_relaxed(l.block_state + (bb - 1 - lane)) : kFlagPrefix;
+            continue;
+        }
+        const uint64_t v = ((1u << lane) & upto) ? (lbB & kValueMask) : 0;
+        excl += warp_sum_u64(v);
+        if (pref) break;
+        bb -= 32;                                            // more than 32 blocks back (cold start only)
+        lbB = (bb - 1 - lane >= 0) ? ld_relaxed(l.block_state + (bb - 1 - lane)) : kFlagPrefix;
+    }
+    if (lane == 0) {
+        const uint64_t incl = (excl + agg) & kValueMask;
+        st_relaxed(l.tile_state + tile, kFlagPrefix | incl);
+        if (i == 31) atomicMax((unsigned long long *)(l.block_state + b), kFlagPrefix | incl);
+    }
+    return excl;
+}
+
+// Software pipeline (per CTA): front(T+2) | look-back loads(T+1) | main(T)
+//   front : take a ticket, load 64 B/thread from HBM, newline mask, block scan, publish the tile's count
+//   main  : re-load the bytes (L2 hit), resolve the prefix (loads issued one stage earlier), walk + encode,
+//           k-mer stage (which overlaps the HBM loads of the next front)
 template <int MODE, int ENC, bool SMEM_HIST, bool MINIMIZER>
 __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -167,11 +242,11 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
     uint8_t *s_lut = s_nl0 + kNl0Bytes;                            // 256
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_lut + 256);  // n_bins (SMEM_HIST)
     __shared__ int64_t s_line_base;
-    __shared__ int64_t s_ticket;
+    __shared__ int64_t s_tk[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_halo = tid >= kMainThreads;
-    uint64_t *tile_state = ws_tile_state(a.ws);
+    const LookbackArrays lb = lookback_arrays(a.ws, a.n_tiles_total);
     const bool cr = a.status[BNPK_ST_CR] != 0;
 
     if (MODE == 1) {
@@ -191,28 +266,20 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
     ht.mask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
     ht.delta = 1ull;
     uint64_t acc_bases = 0, acc_values = 0;     // per-thread statistics, flushed once
-    // lines_per_entry is a power of two (2 or 4): phases and entry indices are masks and shifts
+    // lines_per_entry is a power of two (1, 2 or 4): phases and entry indices are masks and shifts
     const uint32_t ls = (uint32_t)a.lpe_shift, pm = (1u << ls) - 1u;
     const uint32_t fl = (uint32_t)a.field_line;
     const uint32_t want = (fl - 1u) & pm;                          // phase of the newline before the field line
+    const int my0 = tid * 64;                                       // first staged byte of this thread
     uint32_t iter = 0;
-    __syncthreads();
 
-    while (true) {
-        if (tid == 0) s_ticket = a.tile_begin + (int64_t)atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
-        __syncthreads();
-        const int64_t tile = s_ticket;
-        if (tile >= a.tile_end) break;
-        ++iter;
-        const uint32_t tag = (iter & 0xFFFFu) << 16;
+    auto staged_len_of = [&](int64_t tile) -> int {
         const size_t byte0 = (size_t)tile * kTileBytes;
-        const int tile_len = (int)min((size_t)kTileBytes, a.n - byte0);
-        const int staged_len = (MODE == 1) ? (int)min((size_t)(kTileBytes + kHaloBytes), a.n - byte0) : tile_len;
-        const int my0 = tid * 64;                                   // first staged byte of this thread
-
-        // ---- 1. load my 64 bytes, newline mask ------------------------------------------------
-        uint32_t raw[16];
-        uint64_t nlmask = 0;
+        return (MODE == 1) ? (int)min((size_t)(kTileBytes + kHaloBytes), a.n - byte0) : (int)min((size_t)kTileBytes, a.n - byte0);
+    };
+    auto load_raw = [&](int64_t tile, uint32_t *raw) {
+        const size_t byte0 = (size_t)tile * kTileBytes;
+        const int staged_len = staged_len_of(tile);
         if (my0 < staged_len) {
             const uint8_t *p = a.chunk + byte0 + my0;
             if (my0 + 64 <= staged_len && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
@@ -225,14 +292,19 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                     raw[4 * u] = q.x; raw[4 * u + 1] = q.y; raw[4 * u + 2] = q.z; raw[4 * u + 3] = q.w;
                 }
             }
-            nlmask = eq_mask64(raw, 0x0A0A0A0Au);
-            if (my0 + 64 > staged_len) nlmask &= (~0ull) >> (64 - (staged_len - my0));
         }
-        if (cr) s_nl0[tid] = (uint8_t)(nlmask & 1ull);
-
-        // ---- 2. block scan of newline counts (halo warp included), look-back over the tile proper
-        const uint32_t my_cnt = (uint32_t)__popcll(nlmask);
-        uint32_t inc = my_cnt;
+    };
+    // front end of one tile: newline mask, block scan, publish the tile's newline count.
+    // (two __syncthreads; must be called by every thread)
+    auto front = [&](int64_t tile, const uint32_t *raw, uint64_t &nl, uint32_t &ex, uint32_t &tnl) {
+        const int staged_len = staged_len_of(tile);
+        nl = 0;
+        if (my0 < staged_len) {
+            nl = eq_mask64(raw, 0x0A0A0A0Au);
+            if (my0 + 64 > staged_len) nl &= (~0ull) >> (64 - (staged_len - my0));
+        }
+        const uint32_t cnt = (uint32_t)__popcll(nl);
+        uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -249,19 +321,55 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 if (lane >= o) winc += t;
             }
             if (lane < kCtaWarps) s_warp[lane] = winc - w;           // exclusive warp prefix
-            // newlines of the tile proper = everything before the halo warp(s)
-            const uint32_t tile_nl_w = __shfl_sync(0xffffffffu, winc, kMainThreads / 32 - 1);
-            const uint64_t excl = (a.debug & 1) ? (uint64_t)tile * 208ull : lookback_exclusive(tile_state, tile, tile_nl_w, lane);
+            const uint32_t tile_nl_w = __shfl_sync(0xffffffffu, winc, kMainThreads / 32 - 1);   // tile proper only
             if (lane == 0) {
-                s_line_base = (int64_t)excl;
                 s_misc[3] = tile_nl_w;
-                s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; s_misc[4] = 0xFFFFFFFFu;
+                lookback_publish(lb, tile, tile_nl_w);
             }
         }
         __syncthreads();
+        ex = s_warp[warp] + inc - cnt;
+        tnl = s_misc[3];
+    };
+    auto take_ticket = [&]() -> int64_t {
+        return a.tile_begin + (int64_t)atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
+    };
+
+    // ---- prologue: fill the pipeline ---------------------------------------------------------
+    if (tid == 0) { s_tk[0] = take_ticket(); s_tk[1] = take_ticket(); s_tk[2] = take_ticket(); }
+    __syncthreads();
+    int64_t tM = s_tk[0], tP = s_tk[1], tF = s_tk[2];
+    uint32_t raw[16];
+    uint64_t nlM = 0, nlP = 0, lbA = kFlagPrefix, lbB = kFlagPrefix;
+    uint32_t exM = 0, exP = 0, tnlM = 0, tnlP = 0;
+    if (tM < a.tile_end) { load_raw(tM, raw); front(tM, raw, nlM, exM, tnlM); }
+    if (tP < a.tile_end) { load_raw(tP, raw); front(tP, raw, nlP, exP, tnlP); }
+    if (warp == 0 && tM < a.tile_end) lookback_issue(lb, tM, lane, lbA, lbB);
+
+    while (tM < a.tile_end) {
+        const int64_t tile = tM;
+        ++iter;
+        const uint32_t tag = (iter & 0xFFFFu) << 16;
+        const size_t byte0 = (size_t)tile * kTileBytes;
+        const int tile_len = (int)min((size_t)kTileBytes, a.n - byte0);
+        const int staged_len = staged_len_of(tile);
+        const uint64_t nlmask = nlM;
+        const uint32_t my_excl = exM, tile_nl = tnlM;
+
+        // ---- 1. main: re-load my bytes (L2), resolve the prefix, ask for the next ticket ---------
+        if (MODE == 1) load_raw(tile, raw);
+        int64_t next_ticket = 0;
+        if (tid == 0) next_ticket = take_ticket();
+        if (cr) s_nl0[tid] = (uint8_t)(nlmask & 1ull);
+        if (warp == 0) {
+            const uint64_t excl = lookback_finish(lb, tile, tile_nl, lane, lbA, lbB);
+            if (lane == 0) {
+                s_line_base = (int64_t)excl;
+                s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; s_misc[4] = 0xFFFFFFFFu;
+            }
+        }
+        __syncthreads();                                             // S1
         const int64_t line_base = s_line_base;
-        const uint32_t tile_nl = s_misc[3];
-        const uint32_t my_excl = s_warp[warp] + inc - my_cnt;       // tile-relative line index of my first byte
 
         // 32-bit, tile-relative line arithmetic: global line = line_base + rel
         const uint32_t base_phase = (uint32_t)line_base & pm;
@@ -271,7 +379,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         const int64_t r_first = q0 + r_first_off;
         const int n_rows_tile = (tile_nl > jr0) ? (int)(((tile_nl - 1u - jr0) >> ls) + 1u) : 0;
 
-        // ---- 3. one walk over my newlines: sequence-byte mask + row starts/ends + validation ----
+        // ---- 2. one walk over my newlines: sequence-byte mask + row starts/ends + validation ----
         uint64_t seqmask = 0;
         uint32_t my_complete = 0;
         auto walk = [&](const int round, const bool first_round) {
@@ -290,7 +398,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 if (b >= 64) break;
                 // ---- the newline at bit b ends line `rel`
                 const int p = my0 + b;                               // tile-relative position
-                if (first_round && !is_halo && !(a.debug & 2)) {
+                if (first_round && !is_halo) {
                     if (phase == pm) {                                // last line of an entry
                         my_complete = p + 1;
                         const size_t gp = byte0 + p;
@@ -357,7 +465,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 seqmask &= ~(crmask & next_nl);
             }
             if (my0 + 64 > staged_len) seqmask = (my0 < staged_len) ? (seqmask & ((~0ull) >> (64 - (staged_len - my0)))) : 0;
-            // ---- 4. encode + validate only the units that hold sequence bytes -------------------
+            // ---- 3. encode + validate only the units that hold sequence bytes -------------------
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t seq16 = (uint32_t)(seqmask >> (16 * u)) & 0xFFFFu;
@@ -376,14 +484,18 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 atomicSub((unsigned int *)&a.lens[0], (unsigned int)a.start_offset);
             }
         }
-        __syncthreads();
+        __syncthreads();                                             // S2: packed stream and row list complete
 
-        // ---- 5. rows -> histogram ----------------------------------------------------------------
+        // ---- 4. start the next front-end load (HBM) and the look-back loads of the pending tile ---
+        if (tF < a.tile_end) load_raw(tF, raw);
+        if (warp == 0 && tP < a.tile_end) lookback_issue(lb, tP, lane, lbA, lbB);
+
+        // ---- 5. rows -> histogram (overlaps the loads above) --------------------------------------
         if (MODE == 1) {
             auto defer_row = [&](uint64_t start, uint64_t r) {
                 const unsigned long long d = atomicAdd((unsigned long long *)(a.ws + kWsDeferred), 1ull);
                 if (d < a.deferred_cap) {
-                    uint64_t *def = ws_deferred(a.ws, a.n_tiles_total);
+                    uint64_t *def = a.deferred;
                     def[2 * d] = start;
                     def[2 * d + 1] = r;
                 } else {
@@ -505,9 +617,18 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                     }
                 }
             }
+        }
+        // ---- 6. front end of tile F (its bytes were requested in step 4); rotate the pipeline --------
+        if (tid == 0) s_tk[0] = next_ticket;
+        uint64_t nlF = 0;
+        uint32_t exF = 0, tnlF = 0;
+        if (tF < a.tile_end) {
+            front(tF, raw, nlF, exF, tnlF);                           // two __syncthreads inside
+        } else {
             __syncthreads();
         }
-        // ---- 6. per-tile global bookkeeping (one atomic each) -----------------------------------
+        // per-tile global bookkeeping of the tile just finished (one atomic each; all its shared-memory
+        // atomics are ordered before the barrier(s) above)
         if (tid == 0) {
             if (s_misc[0]) atomicMax((unsigned long long *)&a.status[BNPK_ST_N_COMPLETE_BYTES], (unsigned long long)(byte0 + s_misc[0]));
             if (MODE == 1 && s_misc[1]) {
@@ -516,7 +637,9 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             }
             if (tile == a.n_tiles_total - 1) a.status[BNPK_ST_N_LINES] = line_base + tile_nl;
         }
-        if (MODE == 0) __syncthreads();
+        tM = tP; nlM = nlP; exM = exP; tnlM = tnlP;
+        tP = tF; nlP = nlF; exP = exF; tnlP = tnlF;
+        tF = s_tk[0];
     }
 
     // ---- flush ---------------------------------------------------------------------------------
@@ -592,9 +715,11 @@ static int launch_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStr
 
 static size_t deferred_capacity(size_t n) { return n / kHaloBytes + n / 1024 + 16; }
 
+// workspace (uint64 words): header | tile_state[n_tiles+1] | block_cnt[nb] | block_state[nb] | deferred[2*cap]
+static size_t ws_lookback_words(size_t n_tiles) { return kWsHeaderWords + (n_tiles + 1) + 2 * ((n_tiles >> 5) + 2); }
 size_t tile_workspace_bytes(size_t n) {
-    const size_t n_tiles = (n + kTileBytes - 1) / kTileBytes + 1;
-    return (kWsHeaderWords + n_tiles + 2 * deferred_capacity(n)) * sizeof(uint64_t);
+    const size_t n_tiles = (n + kTileBytes - 1) / kTileBytes;
+    return (ws_lookback_words(n_tiles) + 2 * deferred_capacity(n)) * sizeof(uint64_t);
 }
 
 bool use_smem_hist(int64_t n_bins, int hist_mode) {
@@ -630,9 +755,10 @@ int chunk_kmer_count_impl(const uint8_t *chunk, size_t n, size_t slice_begin, si
     a.lpe = lpe; a.lpe_shift = lpe == 4 ? 2 : 1; a.field_line = 1; a.start_offset = 0; a.header_char = header_char;
     a.check_plus = check_plus; a.status = status; a.ws = (uint64_t *)workspace; a.n_tiles_total = n_tiles_total;
     a.deferred_cap = deferred_capacity(n);
+    a.deferred = (uint64_t *)workspace + ws_lookback_words((size_t)n_tiles_total);
     a.lut = lut256; a.k = k; a.window = window; a.n_bins = (uint64_t)n_bins; a.hist = (unsigned long long *)hist;
     if (slice_begin == 0) {
-        BNPK_CUDA(cudaMemsetAsync(workspace, 0, (kWsHeaderWords + n_tiles_total + 1) * sizeof(uint64_t), st));
+        BNPK_CUDA(cudaMemsetAsync(workspace, 0, ws_lookback_words((size_t)n_tiles_total) * sizeof(uint64_t), st));
         cr_detect_kernel<<<1, 32, 0, st>>>(chunk, std::min(n, slice_end), lpe, trim_cr, status);
         BNPK_LAUNCHED("cr_detect_kernel");
     }
@@ -644,8 +770,7 @@ int chunk_kmer_count_impl(const uint8_t *chunk, size_t n, size_t slice_begin, si
         finalize_status_kernel<<<1, 32, 0, st>>>(status, lpe);
         BNPK_LAUNCHED("finalize_status_kernel");
         rc = count_fixups_impl(chunk, n, lpe, enc_mode, lut256, k, window, n_bins, hist, status,
-                               (uint64_t *)workspace + kWsDeferred,
-                               (uint64_t *)workspace + kWsHeaderWords + n_tiles_total, a.deferred_cap, st);
+                               (uint64_t *)workspace + kWsDeferred, a.deferred, a.deferred_cap, st);
     }
     return rc;
 }
@@ -665,7 +790,7 @@ int line_split_impl(const uint8_t *chunk, size_t n, int lpe, int field_line, int
     a.header_char = header_char; a.check_plus = check_plus; a.status = status; a.ws = (uint64_t *)workspace;
     a.starts = starts; a.lens = lens; a.max_rows = max_rows; a.n_bins = 1;
     if (max_rows) BNPK_CUDA(cudaMemsetAsync(lens, 0, max_rows * sizeof(int32_t), st));
-    BNPK_CUDA(cudaMemsetAsync(workspace, 0, (kWsHeaderWords + a.n_tiles_total + 1) * sizeof(uint64_t), st));
+    BNPK_CUDA(cudaMemsetAsync(workspace, 0, ws_lookback_words((size_t)a.n_tiles_total) * sizeof(uint64_t), st));
     cr_detect_kernel<<<1, 32, 0, st>>>(chunk, n, lpe, trim_cr, status);
     BNPK_LAUNCHED("cr_detect_kernel");
     int rc = launch_tile<0, BNPK_ENC_ASCII_ACGT, false, false>(a, st);
