@@ -233,14 +233,15 @@ __device__ __forceinline__ uint64_t lookback_finish(const LookbackArrays &l, int
 template <int MODE, int ENC, bool SMEM_HIST, bool MINIMIZER>
 __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_codes = smem;                                      // kStagedUnits + 4
+    // layout: [private histogram (n_bins u32, SMEM_HIST only)] [packed stream] [row list] [small stuff]
+    uint32_t *s_hist = smem;                                       // n_bins (SMEM_HIST) -- offset 0: immediate addressing
+    uint32_t *s_codes = smem + ((MODE == 1 && SMEM_HIST) ? a.n_bins : 0);   // kStagedUnits + 4
     uint32_t *s_row_end = s_codes + kStagedUnits + 4;              // kRowCap (tag << 16 | end)
     uint16_t *s_row_start = reinterpret_cast<uint16_t *>(s_row_end + kRowCap);     // kRowCap
     uint32_t *s_warp = reinterpret_cast<uint32_t *>(s_row_start + kRowCap);        // 32
     uint32_t *s_misc = s_warp + 32;                                // 16
     uint8_t *s_nl0 = reinterpret_cast<uint8_t *>(s_misc + 16);     // kNl0Bytes, '\r' mode only
     uint8_t *s_lut = s_nl0 + kNl0Bytes;                            // 256
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_lut + 256);  // n_bins (SMEM_HIST)
     __shared__ int64_t s_line_base;
     __shared__ int64_t s_tk[3];
 
@@ -335,15 +336,17 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         return a.tile_begin + (int64_t)atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
     };
 
-    // ---- prologue: fill the pipeline ---------------------------------------------------------
+    // ---- prologue: fill the pipeline: all three first tickets are counted and published before any
+    // main stage runs, so no CTA ever waits for a neighbour's main stage ------------------------------
     if (tid == 0) { s_tk[0] = take_ticket(); s_tk[1] = take_ticket(); s_tk[2] = take_ticket(); }
     __syncthreads();
     int64_t tM = s_tk[0], tP = s_tk[1], tF = s_tk[2];
     uint32_t raw[16];
-    uint64_t nlM = 0, nlP = 0, lbA = kFlagPrefix, lbB = kFlagPrefix;
-    uint32_t exM = 0, exP = 0, tnlM = 0, tnlP = 0;
+    uint64_t nlM = 0, nlP = 0, nlF = 0, lbA = kFlagPrefix, lbB = kFlagPrefix;
+    uint32_t exM = 0, exP = 0, exF = 0, tnlM = 0, tnlP = 0, tnlF = 0;
     if (tM < a.tile_end) { load_raw(tM, raw); front(tM, raw, nlM, exM, tnlM); }
     if (tP < a.tile_end) { load_raw(tP, raw); front(tP, raw, nlP, exP, tnlP); }
+    if (tF < a.tile_end) { load_raw(tF, raw); front(tF, raw, nlF, exF, tnlF); }
     if (warp == 0 && tM < a.tile_end) lookback_issue(lb, tM, lane, lbA, lbB);
 
     while (tM < a.tile_end) {
@@ -484,10 +487,12 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 atomicSub((unsigned int *)&a.lens[0], (unsigned int)a.start_offset);
             }
         }
+        if (tid == 0) s_tk[0] = next_ticket;
         __syncthreads();                                             // S2: packed stream and row list complete
 
         // ---- 4. start the next front-end load (HBM) and the look-back loads of the pending tile ---
-        if (tF < a.tile_end) load_raw(tF, raw);
+        const int64_t tN = s_tk[0];
+        if (tN < a.tile_end) load_raw(tN, raw);
         if (warp == 0 && tP < a.tile_end) lookback_issue(lb, tP, lane, lbA, lbB);
 
         // ---- 5. rows -> histogram (overlaps the loads above) --------------------------------------
@@ -525,19 +530,26 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 };
                 if (a.debug & 8) {
                 } else if constexpr (!MINIMIZER) {
-                    const int sub = tid & 3, grp = tid >> 2;
+                    // four threads per row, 32 consecutive k-mers each.  The sub-row index is (almost) uniform
+                    // per warp so that threads with a full set of 32 positions run the unpredicated loop.
+                    constexpr int kGroups = kCtaThreads / 4;
+                    const int sub = tid / kGroups, grp = tid - sub * kGroups;
                     const uint64_t kmask = (1ull << (2 * a.k)) - 1;
-                    const bool fast = ht.mask && ht.mask <= 0xFFFFFFFFull;
-                    const uint32_t m32 = (uint32_t)(ht.mask & kmask);
-                    for (int slot0 = 0; slot0 < rows_here; slot0 += kCtaThreads / 4) {
+                    const bool fast = ht.mask && ht.mask <= 0x3FFFFFFFull;
+                    const uint32_t m32x4 = (uint32_t)(ht.mask & kmask) << 2;      // byte offset mask into the table
+                    for (int slot0 = 0; slot0 < rows_here; slot0 += kGroups) {
                         const int slot = slot0 + grp;
-                        int b0 = 0, L = 0;
-                        bool ok = false;
-                        if (sub == 0 && slot < rows_here) ok = row_bounds(slot, b0, L);
-                        ok = __shfl_sync(0xffffffffu, ok, lane & ~3);
-                        b0 = __shfl_sync(0xffffffffu, b0, lane & ~3);
-                        L = __shfl_sync(0xffffffffu, L, lane & ~3);
-                        if (!ok) continue;
+                        if (slot >= rows_here) continue;
+                        int b0, L;
+                        {
+                            b0 = s_row_start[slot];
+                            const uint32_t ew = s_row_end[slot];
+                            if ((ew & 0xFFFF0000u) != tag) {            // no terminating newline in the staged region
+                                if (sub == 0 && byte0 + staged_len < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + slot_lo + slot));
+                                continue;                               // (else: unterminated last line, not an entry)
+                            }
+                            L = (int)(ew & 0xFFFFu) - b0;
+                        }
                         if (sub == 0) {
                             acc_bases += (uint64_t)L;
                             atomicMax(&s_misc[1], (uint32_t)b0 + 1u);
@@ -548,24 +560,41 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                             const int n_here = min(32, npos - p0);
                             acc_values += (uint64_t)n_here;
                             if (fast) {
+                                // stream pre-shifted left by 2 bits: (window & mask) is directly the byte offset
                                 const uint32_t bit = 2u * (uint32_t)(b0 + p0);
                                 const uint32_t idx = bit >> 5, sh = bit & 31u;
                                 const uint32_t w0 = s_codes[idx], w1 = s_codes[idx + 1], w2 = s_codes[idx + 2], w3 = s_codes[idx + 3];
-                                const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+                                const uint32_t c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh), c2 = __funnelshift_r(w2, w3, sh);
+                                const uint32_t a0 = c0 << 2, a1 = __funnelshift_l(c0, c1, 2), a2 = __funnelshift_l(c1, c2, 2);
+                                if (n_here == 32) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32;
-                                    if (j < n_here) {
-                                        if constexpr (SMEM_HIST) atomicAdd(s_hist + v, 1u);
-                                        else atomicAdd(a.hist + v, 1ull);
+                                    for (int j = 0; j < 16; ++j) {
+                                        const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32x4;
+                                        if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
+                                        else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
                                     }
-                                }
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32;
-                                    if (j + 16 < n_here) {
-                                        if constexpr (SMEM_HIST) atomicAdd(s_hist + v, 1u);
-                                        else atomicAdd(a.hist + v, 1ull);
+                                    for (int j = 0; j < 16; ++j) {
+                                        const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32x4;
+                                        if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
+                                        else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) {
+                                        const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32x4;
+                                        if (j < n_here) {
+                                            if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
+                                            else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                        }
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) {
+                                        const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32x4;
+                                        if (j + 16 < n_here) {
+                                            if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
+                                            else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                        }
                                     }
                                 }
                             } else {
@@ -618,12 +647,11 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 }
             }
         }
-        // ---- 6. front end of tile F (its bytes were requested in step 4); rotate the pipeline --------
-        if (tid == 0) s_tk[0] = next_ticket;
-        uint64_t nlF = 0;
-        uint32_t exF = 0, tnlF = 0;
-        if (tF < a.tile_end) {
-            front(tF, raw, nlF, exF, tnlF);                           // two __syncthreads inside
+        // ---- 6. front end of the new tile (its bytes were requested in step 4); rotate the pipeline ----
+        uint64_t nlN = 0;
+        uint32_t exN = 0, tnlN = 0;
+        if (tN < a.tile_end) {
+            front(tN, raw, nlN, exN, tnlN);                           // two __syncthreads inside
         } else {
             __syncthreads();
         }
@@ -639,7 +667,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         }
         tM = tP; nlM = nlP; exM = exP; tnlM = tnlP;
         tP = tF; nlP = nlF; exP = exF; tnlP = tnlF;
-        tF = s_tk[0];
+        tF = tN; nlF = nlN; exF = exN; tnlF = tnlN;
     }
 
     // ---- flush ---------------------------------------------------------------------------------
