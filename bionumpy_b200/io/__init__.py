@@ -3,3 +3,4 @@ from .buffers import (CudaFastQBuffer, CudaTwoLineFastaBuffer, CudaOneLineBuffer
 from .exceptions import FormatException, IncompleteEntryException
 from .files import bnp_open
 from .parser import CudaFileReader, NpDataclassReader
+from .multiline import CudaMultiLineFastaBuffer, MultiLineFastaBuffer

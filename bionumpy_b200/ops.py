@@ -134,10 +134,11 @@ def rows_encode(base, starts, lens, enc_mode, lut=None, offsets=None, status=Non
     return out, offsets, status
 
 
-def rows_kmer_hash(base, starts, lens, enc_mode, k, lut=None, offsets=None, status=None):
+def rows_kmer_hash(base, starts, lens, enc_mode, k, lut=None, offsets=None, status=None, total=None):
     if offsets is None:
         offsets = row_offsets(lens, k - 1)
-    total = int(offsets[-1].item())
+    if total is None:
+        total = int(offsets[-1].item())
     out = torch.empty(total, dtype=torch.int64, device=base.device)
     if status is None:
         status = nv.new_status(base.device)
@@ -146,10 +147,11 @@ def rows_kmer_hash(base, starts, lens, enc_mode, k, lut=None, offsets=None, stat
     return out, offsets, status
 
 
-def rows_minimizers(base, starts, lens, enc_mode, k, window_size, lut=None, offsets=None, status=None):
+def rows_minimizers(base, starts, lens, enc_mode, k, window_size, lut=None, offsets=None, status=None, total=None):
     if offsets is None:
         offsets = row_offsets(lens, window_size - 1)
-    total = int(offsets[-1].item())
+    if total is None:
+        total = int(offsets[-1].item())
     out = torch.empty(total, dtype=torch.int64, device=base.device)
     if status is None:
         status = nv.new_status(base.device)

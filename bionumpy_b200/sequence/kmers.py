@@ -57,6 +57,28 @@ def _source_of(sequence) -> _Source:
     return _Source(data, starts, lens, nv.ENC_CODES, None, enc)
 
 
+LONG_ROW = 1 << 14          # rows longer than this are cut into overlapping pieces, one warp each
+
+
+def _split_long_rows(starts, lens, span, out_offsets=None, piece=LONG_ROW):
+    """Rows longer than ``piece`` positions become pieces [i*piece, (i+1)*piece + span - 1): every k-mer /
+    window start belongs to exactly one piece, so counts and (with ``out_offsets``) materialised values are
+    unchanged while long rows (chromosomes) spread over many warps.  Index arithmetic only (torch);
+    returns (starts, lens, out_offsets) of the pieces."""
+    L = lens.to(torch.int64)
+    if L.numel() == 0 or int(L.max().item()) <= piece + span - 1:
+        return starts, lens, out_offsets
+    n_pos = torch.clamp(L - (span - 1), min=0)                       # window starts per row
+    n_pieces = torch.clamp((n_pos + piece - 1) // piece, min=1)
+    row = torch.repeat_interleave(torch.arange(L.numel(), device=L.device), n_pieces)
+    first = torch.cumsum(n_pieces, 0) - n_pieces
+    idx = torch.arange(row.numel(), device=L.device) - first[row]    # piece index inside its row
+    p_start = starts[row] + idx * piece
+    p_len = torch.minimum(L[row] - idx * piece, torch.full_like(idx, piece + span - 1))
+    p_off = None if out_offsets is None else out_offsets[:-1][row] + idx * piece
+    return p_start.contiguous(), p_len.to(torch.int32).contiguous(), p_off
+
+
 class LazyKmerValues(EncodedRaggedArray):
     """EncodedRaggedArray of k-mer hashes / minimizers whose int64 data appear on first use."""
 
@@ -78,12 +100,19 @@ class LazyKmerValues(EncodedRaggedArray):
             s = self._source
             shrink = (self._window if self._window else self._k) - 1
             offsets = ops.row_offsets(s.lens, shrink)
-            if self._window:
-                vals, _, status = ops.rows_minimizers(s.base, s.starts, s.lens, s.enc_mode, self._k, self._window,
-                                                      s.lut, offsets)
+            p_starts, p_lens, p_off = _split_long_rows(s.starts, s.lens, shrink + 1, offsets)
+            if p_off is not None and p_off is not offsets:
+                total = int(offsets[-1].item())
+                p_off = torch.cat([p_off, offsets[-1:]]).contiguous()   # kernels read offsets[row] only
             else:
-                vals, _, status = ops.rows_kmer_hash(s.base, s.starts, s.lens, s.enc_mode, self._k, s.lut, offsets)
-            self._check(status)
+                total, p_off = None, offsets
+            if self._window:
+                vals, _, status = ops.rows_minimizers(s.base, p_starts, p_lens, s.enc_mode, self._k, self._window,
+                                                      s.lut, p_off, total=total)
+            else:
+                vals, _, status = ops.rows_kmer_hash(s.base, p_starts, p_lens, s.enc_mode, self._k, s.lut, p_off,
+                                                     total=total)
+            self._check(status, split=p_starts is not s.starts)
             self._lazy = vals
         return self._lazy
 
@@ -94,8 +123,13 @@ class LazyKmerValues(EncodedRaggedArray):
     def is_materialised(self):
         return self._lazy is not None
 
-    def _check(self, status):
+    def _check(self, status, split=False):
         bad = ops.read_status(status).bad_base()
+        if bad is not None and split:
+            # the (row, position) refers to a piece of a long row: recompute on the unsplit rows (error path)
+            s = self._source
+            _, status = ops.rows_kmer_count(s.base, s.starts, s.lens, s.enc_mode, 1, 4, 0, s.lut)
+            bad = ops.read_status(status).bad_base()
         if bad is not None:
             logging.error("Tried to change encoding of sequences to DNAEncoding, but failed. "
                           "Make sure your sequences are valid DNA, only containing A, C, G, and T")
@@ -107,8 +141,10 @@ class LazyKmerValues(EncodedRaggedArray):
         buf = s.chunk_buffer
         if buf is not None and buf.can_fuse_count():
             return buf.fused_kmer_histogram(self._k, self._window, n_bins, s.enc_mode, s.lut)
-        hist, status = ops.rows_kmer_count(s.base, s.starts, s.lens, s.enc_mode, self._k, n_bins, self._window, s.lut)
-        self._check(status)
+        span = self._window if self._window else self._k
+        p_starts, p_lens, _ = _split_long_rows(s.starts, s.lens, span)
+        hist, status = ops.rows_kmer_count(s.base, p_starts, p_lens, s.enc_mode, self._k, n_bins, self._window, s.lut)
+        self._check(status, split=p_starts is not s.starts)
         return hist
 
 

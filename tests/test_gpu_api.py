@@ -273,3 +273,60 @@ def test_count_kmers_hashed_matches_oracle(bnp, big_fq_bytes, big_fq_path):
         codes = o.encode_flat(o.gather_rows(big_fq_bytes, st[10:500, 1], ln[10:500, 1]), o.alphabet_lut())
         vals = o.get_minimizers_fast(codes, ln[10:500, 1], k, w)[0] if w else o.get_kmers(codes, ln[10:500, 1], k)[0]
         assert np.array_equal(bnp.count_kmers_hashed(sub, k, B, window_size=w).cpu().numpy(), o.count_bucketed_flat(vals, B))
+
+
+# ---- multi-line FASTA (config 4: long ragged rows) -------------------------------------------------------
+def _write_fasta(path, rng, lengths, width=50, eol="\n"):
+    seqs = []
+    with open(path, "w", newline="") as f:
+        for i, L in enumerate(lengths):
+            s = "".join(rng.choice(list("ACGT"), size=L))
+            seqs.append(s)
+            f.write(f">chr{i} some description{eol}")
+            for a in range(0, L, width):
+                f.write(s[a:a + width] + eol)
+    return seqs
+
+
+def test_multiline_fasta_fixture(bnp, tmp_path):
+    """tests/buffers.py:27-35,116-118 and tests/test_io.py:213-249 (carriage returns)."""
+    p = tmp_path / "m.fa"
+    p.write_text(">header\nCTTGCC\nGCCTCC\n>header2\nCCCCCC\nGGGCCC\nTTT\n")
+    data = bnp.open(str(p)).read()
+    assert data.sequence.tolist() == ["CTTGCCGCCTCC", "CCCCCCGGGCCCTTT"] and data.name.tolist() == ["header", "header2"]
+    for size in (5000000, 30):
+        seqs = sum((c.sequence.tolist() for c in bnp.open(str(p)).read_chunks(size)), [])
+        assert seqs == ["CTTGCCGCCTCC", "CCCCCCGGGCCCTTT"], size
+    q = tmp_path / "cr.fa"
+    q.write_bytes(b">test_sequence_id_here\r\nGACTG\r\n>test_sequence_id_here2\r\nGACTC\r\nGAG\r\n")
+    assert bnp.open(str(q)).read().sequence.tolist() == ["GACTG", "GACTCGAG"]
+
+
+def test_genome_like_fasta_k21(bnp, tmp_path):
+    """BASELINE config 4 in miniature: chromosome-length rows, k = 21, hashed buckets + exact distinct counts."""
+    from oracle import bnp_oracle as o
+    rng = np.random.default_rng(11)
+    lengths = [230_218, 81_317, 5, 0, 123_456, 20]
+    path = tmp_path / "genome.fa"
+    seqs = _write_fasta(path, rng, lengths)
+    codes = o.encode_flat(np.frombuffer("".join(seqs).encode(), dtype=np.uint8), o.alphabet_lut())
+    want_h, want_l = o.get_kmers(codes, np.array(lengths), 21)
+    for chunk_size in (5_000_000, 100_000):
+        hist = None
+        n_entries = 0
+        for chunk in bnp.open(str(path)).read_chunks(chunk_size):
+            n_entries += len(chunk)
+            h = bnp.count_kmers_hashed(chunk.sequence, 21, 1 << 16)
+            hist = h if hist is None else hist + h
+        assert n_entries == len(lengths)
+        assert np.array_equal(hist.cpu().numpy(), o.count_bucketed_flat(want_h, 1 << 16))
+    whole = bnp.open(str(path)).read()
+    assert whole.sequence.lengths.cpu().tolist() == lengths
+    kmers = bnp.get_kmers(whole.sequence, 21)
+    got = kmers.raw().ravel().cpu().numpy()                       # long rows are cut into pieces internally
+    assert np.array_equal(got, want_h) and kmers.lengths.cpu().tolist() == want_l.tolist()
+    u_w, c_w = np.unique(want_h, return_counts=True)
+    u_g, c_g = np.unique(got, return_counts=True)
+    assert np.array_equal(u_w, u_g) and np.array_equal(c_w, c_g)
+    mins = bnp.get_minimizers(bnp.change_encoding(whole.sequence, bnp.DNAEncoding), 21, 31).raw().ravel().cpu().numpy()
+    assert np.array_equal(mins, o.get_minimizers_fast(codes, np.array(lengths), 21, 31)[0])
