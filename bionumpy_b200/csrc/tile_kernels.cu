@@ -149,6 +149,15 @@ constexpr int kCtaWarps = kCtaThreads / 32;
 constexpr int kMainThreads = kTileBytes / 64;
 constexpr int kNl0Bytes = (kCtaThreads + 4 + 15) & ~15;
 static_assert(kCtaThreads % 32 == 0 && kMainThreads % 32 == 0 && kCtaWarps <= 32, "tile geometry");
+// shared-memory layout of the tile kernel, in 32-bit words
+constexpr int kOffCodes = 0;
+constexpr int kOffRowEnd = kOffCodes + kStagedUnits + 4;
+constexpr int kOffRowStart = kOffRowEnd + kRowCap;
+constexpr int kOffWarp = kOffRowStart + kRowCap / 2;
+constexpr int kOffMisc = kOffWarp + 32;
+constexpr int kOffNl0 = kOffMisc + 16;
+constexpr int kOffLut = kOffNl0 + kNl0Bytes / 4;
+constexpr int kOffHist = kOffLut + 64;
 
 // ---- two-level look-back state in the workspace ------------------------------------------------
 //   tile_state[t]  : flag|value, AGG = newlines of tile t, PREFIX = newlines of tiles 0..t
@@ -532,12 +541,13 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 } else if constexpr (!MINIMIZER) {
                     // four threads per row, 32 consecutive k-mers each.  The sub-row index is (almost) uniform
                     // per warp so that threads with a full set of 32 positions run the unpredicated loop.
-                    constexpr int kGroups = kCtaThreads / 4;
+                    // (the main warps do this stage; the halo warp has no share in it)
+                    constexpr int kGroups = kMainThreads / 4;                // 64 groups = 2 warps per sub-row index
                     const int sub = tid / kGroups, grp = tid - sub * kGroups;
                     const uint64_t kmask = (1ull << (2 * a.k)) - 1;
                     const bool fast = ht.mask && ht.mask <= 0x3FFFFFFFull;
                     const uint32_t m32x4 = (uint32_t)(ht.mask & kmask) << 2;      // byte offset mask into the table
-                    for (int slot0 = 0; slot0 < rows_here; slot0 += kGroups) {
+                    for (int slot0 = 0; slot0 < rows_here && sub < 4; slot0 += kGroups) {
                         const int slot = slot0 + grp;
                         if (slot >= rows_here) continue;
                         int b0, L;
@@ -694,8 +704,7 @@ __global__ void finalize_status_kernel(int64_t *status, int lpe) {
 }
 
 static size_t tile_smem_bytes(int mode, uint64_t n_bins, bool smem_hist) {
-    size_t bytes = (size_t)(kStagedUnits + 4) * 4 + (size_t)kRowCap * 4 + (size_t)kRowCap * 2 + 32 * 4 + 16 * 4 +
-                   kNl0Bytes + 256;
+    size_t bytes = (size_t)kOffHist * 4;
     if (mode == 1 && smem_hist) bytes += n_bins * 4;
     return bytes;
 }
