@@ -235,27 +235,30 @@ __device__ __forceinline__ uint64_t lookback_finish(const LookbackArrays &l, int
     return excl;
 }
 
-// Software pipeline (per CTA): front(T+2) | look-back loads(T+1) | main(T)
-//   front : take a ticket, load 64 B/thread from HBM, newline mask, block scan, publish the tile's count
-//   main  : re-load the bytes (L2 hit), resolve the prefix (loads issued one stage earlier), walk + encode,
-//           k-mer stage (which overlaps the HBM loads of the next front)
+// Software pipeline (per CTA): front(T+3) | look-back loads(T+1) | main(T)
+//   front : take a ticket, load 64 B/thread from HBM, exact newline mask, block scan, publish the tile's count
+//   main  : resolve the line prefix (loads issued one stage earlier); every thread drops the positions of its
+//           newlines into a sorted shared list; ONE THREAD PER NEWLINE does validation / field publishing;
+//           rows are read straight off the list (row s starts after newline jr0 + s*lpe and ends at the next one);
+//           four threads per read row load the row's 16-byte units (L2 hits), encode + validate only those,
+//           then walk the packed stream for the k-mers.
+constexpr int kNlCap = 1024;              // newline positions of one staged tile kept in shared memory
+constexpr int kNlStep = kNlCap - 8;       // window advance when a tile holds more (lines shorter than ~18 bytes)
+
 template <int MODE, int ENC, bool SMEM_HIST, bool MINIMIZER>
 __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
-    // layout: [private histogram (n_bins u32, SMEM_HIST only)] [packed stream] [row list] [small stuff]
-    uint32_t *s_hist = smem;                                       // n_bins (SMEM_HIST) -- offset 0: immediate addressing
-    uint32_t *s_codes = smem + ((MODE == 1 && SMEM_HIST) ? a.n_bins : 0);   // kStagedUnits + 4
-    uint32_t *s_row_end = s_codes + kStagedUnits + 4;              // kRowCap (tag << 16 | end)
-    uint16_t *s_row_start = reinterpret_cast<uint16_t *>(s_row_end + kRowCap);     // kRowCap
-    uint32_t *s_warp = reinterpret_cast<uint32_t *>(s_row_start + kRowCap);        // 32
-    uint32_t *s_misc = s_warp + 32;                                // 16
-    uint8_t *s_nl0 = reinterpret_cast<uint8_t *>(s_misc + 16);     // kNl0Bytes, '\r' mode only
-    uint8_t *s_lut = s_nl0 + kNl0Bytes;                            // 256
+    // layout: [private histogram (n_bins u32, SMEM_HIST only)] [packed stream] [newline list] [small stuff]
+    uint32_t *s_hist = smem;
+    uint32_t *s_codes = smem + ((MODE == 1 && SMEM_HIST) ? a.n_bins : 0);          // kStagedUnits + 4
+    uint16_t *s_nlpos = reinterpret_cast<uint16_t *>(s_codes + kStagedUnits + 4);  // kNlCap
+    uint32_t *s_warp = reinterpret_cast<uint32_t *>(s_nlpos + kNlCap);             // 32
+    uint32_t *s_misc = s_warp + 32;                                                // 16
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_misc + 16);                     // 256
     __shared__ int64_t s_line_base;
     __shared__ int64_t s_tk[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_halo = tid >= kMainThreads;
     const LookbackArrays lb = lookback_arrays(a.ws, a.n_tiles_total);
     const bool cr = a.status[BNPK_ST_CR] != 0;
 
@@ -263,12 +266,8 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         if (ENC == BNPK_ENC_LUT && tid < 256) s_lut[tid] = a.lut[tid];
         if (SMEM_HIST)
             for (uint32_t b = tid; b < a.n_bins; b += kCtaThreads) s_hist[b] = 0;
-        if (tid < 4) s_codes[kStagedUnits + tid] = 0;
+        for (int i = tid; i < kStagedUnits + 4; i += kCtaThreads) s_codes[i] = 0;
     }
-    if (tid == 0) s_nl0[kCtaThreads] = 0;
-    // row-end slots carry a per-iteration tag; shared memory may hold a stale tagged value from an
-    // earlier launch, so start from zero (tag 0 is never used)
-    for (int i = tid; i < kRowCap; i += kCtaThreads) s_row_end[i] = 0;
     HistTarget ht;
     ht.global = a.hist;
     ht.smem = s_hist;
@@ -281,7 +280,6 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
     const uint32_t fl = (uint32_t)a.field_line;
     const uint32_t want = (fl - 1u) & pm;                          // phase of the newline before the field line
     const int my0 = tid * 64;                                       // first staged byte of this thread
-    uint32_t iter = 0;
 
     auto staged_len_of = [&](int64_t tile) -> int {
         const size_t byte0 = (size_t)tile * kTileBytes;
@@ -305,8 +303,9 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         }
     };
     // front end of one tile: newline mask, block scan, publish the tile's newline count.
-    // (two __syncthreads; must be called by every thread)
-    auto front = [&](int64_t tile, const uint32_t *raw, uint64_t &nl, uint32_t &ex, uint32_t &tnl) {
+    // (two __syncthreads; must be called by every thread).  tnl = newlines of the tile proper,
+    // tall = newlines of the whole staged region (tile + halo).
+    auto front = [&](int64_t tile, const uint32_t *raw, uint64_t &nl, uint32_t &ex, uint32_t &tnl, uint32_t &tall) {
         const int staged_len = staged_len_of(tile);
         nl = 0;
         if (my0 < staged_len) {
@@ -332,17 +331,29 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             }
             if (lane < kCtaWarps) s_warp[lane] = winc - w;           // exclusive warp prefix
             const uint32_t tile_nl_w = __shfl_sync(0xffffffffu, winc, kMainThreads / 32 - 1);   // tile proper only
+            const uint32_t all_nl_w = __shfl_sync(0xffffffffu, winc, kCtaWarps - 1);
             if (lane == 0) {
                 s_misc[3] = tile_nl_w;
+                s_misc[5] = all_nl_w;
                 lookback_publish(lb, tile, tile_nl_w);
             }
         }
         __syncthreads();
         ex = s_warp[warp] + inc - cnt;
         tnl = s_misc[3];
+        tall = s_misc[5];
     };
     auto take_ticket = [&]() -> int64_t {
         return a.tile_begin + (int64_t)atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
+    };
+    auto defer_row = [&](uint64_t start, uint64_t r) {
+        const unsigned long long d = atomicAdd((unsigned long long *)(a.ws + kWsDeferred), 1ull);
+        if (d < a.deferred_cap) {
+            a.deferred[2 * d] = start;
+            a.deferred[2 * d + 1] = r;
+        } else {
+            a.status[BNPK_ST_OVERFLOW] = 1;
+        }
     };
 
     // ---- prologue: fill the pipeline: all three first tickets are counted and published before any
@@ -352,219 +363,184 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
     int64_t tM = s_tk[0], tP = s_tk[1], tF = s_tk[2];
     uint32_t raw[16];
     uint64_t nlM = 0, nlP = 0, nlF = 0, lbA = kFlagPrefix, lbB = kFlagPrefix;
-    uint32_t exM = 0, exP = 0, exF = 0, tnlM = 0, tnlP = 0, tnlF = 0;
-    if (tM < a.tile_end) { load_raw(tM, raw); front(tM, raw, nlM, exM, tnlM); }
-    if (tP < a.tile_end) { load_raw(tP, raw); front(tP, raw, nlP, exP, tnlP); }
-    if (tF < a.tile_end) { load_raw(tF, raw); front(tF, raw, nlF, exF, tnlF); }
+    uint32_t exM = 0, exP = 0, exF = 0, tnlM = 0, tnlP = 0, tnlF = 0, tallM = 0, tallP = 0, tallF = 0;
+    if (tM < a.tile_end) { load_raw(tM, raw); front(tM, raw, nlM, exM, tnlM, tallM); }
+    if (tP < a.tile_end) { load_raw(tP, raw); front(tP, raw, nlP, exP, tnlP, tallP); }
+    if (tF < a.tile_end) { load_raw(tF, raw); front(tF, raw, nlF, exF, tnlF, tallF); }
     if (warp == 0 && tM < a.tile_end) lookback_issue(lb, tM, lane, lbA, lbB);
 
     while (tM < a.tile_end) {
         const int64_t tile = tM;
-        ++iter;
-        const uint32_t tag = (iter & 0xFFFFu) << 16;
         const size_t byte0 = (size_t)tile * kTileBytes;
-        const int tile_len = (int)min((size_t)kTileBytes, a.n - byte0);
         const int staged_len = staged_len_of(tile);
-        const uint64_t nlmask = nlM;
-        const uint32_t my_excl = exM, tile_nl = tnlM;
+        const uint32_t tile_nl = tnlM, all_nl = tallM;
 
-        // ---- 1. main: re-load my bytes (L2), resolve the prefix, ask for the next ticket ---------
-        if (MODE == 1) load_raw(tile, raw);
+        // ---- 1. resolve the prefix, ask for the next ticket ------------------------------------------
         int64_t next_ticket = 0;
         if (tid == 0) next_ticket = take_ticket();
-        if (cr) s_nl0[tid] = (uint8_t)(nlmask & 1ull);
         if (warp == 0) {
             const uint64_t excl = lookback_finish(lb, tile, tile_nl, lane, lbA, lbB);
             if (lane == 0) {
                 s_line_base = (int64_t)excl;
-                s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; s_misc[4] = 0xFFFFFFFFu;
+                s_misc[1] = 0; s_misc[2] = 0;
+                s_tk[0] = next_ticket;
             }
         }
-        __syncthreads();                                             // S1
-        const int64_t line_base = s_line_base;
-
-        // 32-bit, tile-relative line arithmetic: global line = line_base + rel
-        const uint32_t base_phase = (uint32_t)line_base & pm;
-        const int64_t q0 = line_base >> ls;                          // entry index of the tile's first line
-        const uint32_t jr0 = (want - base_phase) & pm;               // first newline (rel) that precedes a field line
-        const uint32_t r_first_off = (base_phase + jr0 + 1u) >> ls;
-        const int64_t r_first = q0 + r_first_off;
-        const int n_rows_tile = (tile_nl > jr0) ? (int)(((tile_nl - 1u - jr0) >> ls) + 1u) : 0;
-
-        // ---- 2. one walk over my newlines: sequence-byte mask + row starts/ends + validation ----
-        uint64_t seqmask = 0;
-        uint32_t my_complete = 0;
-        auto walk = [&](const int round, const bool first_round) {
-            uint64_t m = nlmask;
-            uint32_t rel = my_excl;                                  // rel line index of the current segment
-            int prev = 0;
-            const int slot_lo = round * kRowCap;
-            while (true) {
-                const int b = m ? (__ffsll((long long)m) - 1) : 64;
-                const uint32_t phase = (base_phase + rel) & pm;
-                if (MODE == 1 && first_round) {
-                    // bytes [prev, b) lie on line `rel`; rows owned by this tile have 1 <= rel <= tile_nl
-                    if (b > prev && phase == fl && rel - 1u < tile_nl)
-                        seqmask |= (b >= 64 ? ~0ull : ((1ull << b) - 1)) & ~((1ull << prev) - 1);
+        const int n_rounds = all_nl > (uint32_t)kNlCap ? (int)((all_nl - 8u + kNlStep - 1) / kNlStep) : 1;
+        int64_t line_base = 0, tN = 0;
+        for (int round = 0; round < n_rounds; ++round) {
+            // ---- 2. sorted list of the newline positions of this staged tile (window `round`) -------------
+            if (round > 0) __syncthreads();
+            const int win_lo = round * kNlStep;
+            {
+                uint64_t m = nlM;
+                int li = (int)exM - win_lo;
+                while (m) {
+                    const int bit = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if (li >= 0 && li < kNlCap) s_nlpos[li] = (uint16_t)(my0 + bit);
+                    ++li;
                 }
-                if (b >= 64) break;
-                // ---- the newline at bit b ends line `rel`
-                const int p = my0 + b;                               // tile-relative position
-                if (first_round && !is_halo) {
-                    if (phase == pm) {                                // last line of an entry
-                        my_complete = p + 1;
-                        const size_t gp = byte0 + p;
+            }
+            __syncthreads();                                         // S1: prefix, ticket, list (and the previous k-mer stage) done
+            if (round == 0) {
+                line_base = s_line_base;
+                tN = s_tk[0];
+                // start the next front-end load (HBM) and the look-back loads of the pending tile
+                if (tN < a.tile_end) load_raw(tN, raw);
+                if (warp == 0 && tP < a.tile_end) lookback_issue(lb, tP, lane, lbA, lbB);
+            }
+            // 32-bit, tile-relative line arithmetic: global line = line_base + rel
+            const uint32_t base_phase = (uint32_t)line_base & pm;
+            const int64_t q0 = line_base >> ls;                      // entry index of the tile's first line
+            const uint32_t jr0 = (want - base_phase) & pm;           // first newline (rel) that precedes a field line
+            const uint32_t r_first_off = (base_phase + jr0 + 1u) >> ls;
+            const int64_t r_first = q0 + r_first_off;
+            const int n_rows_tile = (tile_nl > jr0) ? (int)(((tile_nl - 1u - jr0) >> ls) + 1u) : 0;
+            const int n_in_win = min((int)all_nl - win_lo, kNlCap);
+            // events owned by this window: newline indices [win_lo, win_lo + kNlStep) (all of them in the last window)
+            const int ev_hi = (round == n_rounds - 1) ? n_in_win : kNlStep;
+
+            // ---- 3. one thread per newline: validation, field publishing (split mode) -----------------
+            for (int i = tid; i < ev_hi; i += kCtaThreads) {
+                const uint32_t gi = (uint32_t)(win_lo + i);           // tile-relative newline index = rel line index
+                const int p = s_nlpos[i];
+                const size_t gp = byte0 + p;
+                const uint32_t phase = (base_phase + gi) & pm;
+                if (gi < tile_nl) {                                   // newline of the tile proper
+                    if (phase == pm) {                                // last line of an entry: next byte starts a header
                         if (gp + 1 < a.n && a.chunk[gp + 1] != a.header_char)      // one_line_buffer.py:155-173
                             atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY],
-                                      (long long)(q0 + ((base_phase + rel + 1u) >> ls)));
+                                      (long long)(q0 + ((base_phase + gi + 1u) >> ls)));
                     }
                     if (a.check_plus && phase == 1u) {                             // fastq_buffer.py:38-45
-                        const size_t gp = byte0 + p;
                         if (gp + 1 < a.n && a.chunk[gp + 1] != '+')
                             atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY],
-                                      (long long)(q0 + ((base_phase + rel) >> ls)));
+                                      (long long)(q0 + ((base_phase + gi) >> ls)));
                     }
-                }
-                if (MODE == 0) {
-                    // split: start and end of the wanted line are published independently;
-                    // lens[r] accumulates (end - start) mod 2^32 from two atomics.
-                    const size_t gp = byte0 + p;
-                    if (phase == want) {
-                        const int64_t r = q0 + ((base_phase + rel + 1u) >> ls);
-                        if ((size_t)r < a.max_rows) {
-                            const int64_t s = (int64_t)gp + 1 + a.start_offset;
-                            a.starts[r] = s;
-                            atomicSub((unsigned int *)&a.lens[r], (unsigned int)(uint64_t)s);
-                        }
-                    }
-                    if (phase == fl) {
-                        const int64_t r = q0 + ((base_phase + rel) >> ls);
-                        if ((size_t)r < a.max_rows) {
-                            int64_t e = (int64_t)gp;
-                            if (cr && gp > 0 && a.chunk[gp - 1] == '\r') e -= 1;
-                            atomicAdd((unsigned int *)&a.lens[r], (unsigned int)(uint64_t)e);
-                        }
-                    }
-                } else {
-                    if (!is_halo && phase == want) {
-                        const int slot = (int)(((base_phase + rel + 1u) >> ls) - r_first_off) - slot_lo;
-                        if (slot >= 0 && slot < kRowCap) s_row_start[slot] = (uint16_t)(p + 1);
-                    }
-                    if (phase == fl) {
-                        const int slot_abs = (int)(((base_phase + rel) >> ls) - r_first_off);
-                        const int slot = slot_abs - slot_lo;
-                        if (slot_abs >= 0 && slot_abs < n_rows_tile && slot >= 0 && slot < kRowCap) {
-                            int e = p;
-                            if (cr && byte0 + p > 0 && a.chunk[byte0 + p - 1] == '\r') e -= 1;
-                            s_row_end[slot] = tag | (uint32_t)e;
-                        }
-                    }
-                }
-                if (b >= 63) break;
-                m &= m - 1;
-                prev = b + 1;
-                ++rel;
-            }
-        };
-        if (my0 < staged_len && !(a.debug & 4)) walk(0, true);
-        if (my_complete) atomicMax(&s_misc[0], my_complete);
-
-        if (MODE == 1) {
-            if (cr && seqmask) {
-                // a '\r' directly before the line's '\n' is not part of the row (one_line_buffer.py:175-182)
-                const uint64_t crmask = eq_mask64(raw, 0x0D0D0D0Du);
-                const uint64_t next_nl = (nlmask >> 1) | ((uint64_t)s_nl0[tid + 1] << 63);
-                seqmask &= ~(crmask & next_nl);
-            }
-            if (my0 + 64 > staged_len) seqmask = (my0 < staged_len) ? (seqmask & ((~0ull) >> (64 - (staged_len - my0)))) : 0;
-            // ---- 3. encode + validate only the units that hold sequence bytes -------------------
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t seq16 = (uint32_t)(seqmask >> (16 * u)) & 0xFFFFu;
-                if (seq16 && !(a.debug & 16)) {
-                    uint32_t bad;
-                    s_codes[tid * 4 + u] = encode_unit_seq<ENC>(raw + 4 * u, seq16, s_lut, bad);
-                    if (bad) atomicMin(&s_misc[4], (uint32_t)(my0 + 16 * u));   // rare: resolved after the tile
-                }
-            }
-        }
-        if (tile == 0 && tid == 0) {
-            if (a.n > 0 && a.chunk[0] != a.header_char)
-                atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
-            if (MODE == 0 && fl == 0 && a.max_rows > 0) {           // the first line has no newline before it
-                a.starts[0] = a.start_offset;
-                atomicSub((unsigned int *)&a.lens[0], (unsigned int)a.start_offset);
-            }
-        }
-        if (tid == 0) s_tk[0] = next_ticket;
-        __syncthreads();                                             // S2: packed stream and row list complete
-
-        // ---- 4. start the next front-end load (HBM) and the look-back loads of the pending tile ---
-        const int64_t tN = s_tk[0];
-        if (tN < a.tile_end) load_raw(tN, raw);
-        if (warp == 0 && tP < a.tile_end) lookback_issue(lb, tP, lane, lbA, lbB);
-
-        // ---- 5. rows -> histogram (overlaps the loads above) --------------------------------------
-        if (MODE == 1) {
-            auto defer_row = [&](uint64_t start, uint64_t r) {
-                const unsigned long long d = atomicAdd((unsigned long long *)(a.ws + kWsDeferred), 1ull);
-                if (d < a.deferred_cap) {
-                    uint64_t *def = a.deferred;
-                    def[2 * d] = start;
-                    def[2 * d + 1] = r;
-                } else {
-                    a.status[BNPK_ST_OVERFLOW] = 1;
-                }
-            };
-            const int n_rounds = (n_rows_tile + kRowCap - 1) / kRowCap;
-            for (int round = 0; round < (n_rounds > 0 ? n_rounds : 1); ++round) {
-                if (round > 0) {
-                    // more rows than the shared row list holds (lines of ~30 bytes or less): redo the walk
-                    // for the next window of slots
-                    __syncthreads();
-                    if (my0 < staged_len) walk(round, false);
-                    __syncthreads();
-                }
-                const int slot_lo = round * kRowCap;
-                const int rows_here = min(kRowCap, n_rows_tile - slot_lo);
-                auto row_bounds = [&](int slot, int &b0, int &L) -> bool {
-                    b0 = s_row_start[slot];
-                    const uint32_t ew = s_row_end[slot];
-                    if ((ew & 0xFFFF0000u) != tag) {                // no terminating newline in the staged region
-                        if (byte0 + staged_len < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + slot_lo + slot));   // long row
-                        return false;                               // (else: unterminated last line, not an entry)
-                    }
-                    L = (int)(ew & 0xFFFFu) - b0;
-                    return true;
-                };
-                if (a.debug & 8) {
-                } else if constexpr (!MINIMIZER) {
-                    // four threads per row, 32 consecutive k-mers each.  The sub-row index is (almost) uniform
-                    // per warp so that threads with a full set of 32 positions run the unpredicated loop.
-                    // (the main warps do this stage; the halo warp has no share in it)
-                    constexpr int kGroups = kMainThreads / 4;                // 64 groups = 2 warps per sub-row index
-                    const int sub = tid / kGroups, grp = tid - sub * kGroups;
-                    const uint64_t kmask = (1ull << (2 * a.k)) - 1;
-                    const bool fast = ht.mask && ht.mask <= 0x3FFFFFFFull;
-                    const uint32_t m32x4 = (uint32_t)(ht.mask & kmask) << 2;      // byte offset mask into the table
-                    for (int slot0 = 0; slot0 < rows_here && sub < 4; slot0 += kGroups) {
-                        const int slot = slot0 + grp;
-                        if (slot >= rows_here) continue;
-                        int b0, L;
-                        {
-                            b0 = s_row_start[slot];
-                            const uint32_t ew = s_row_end[slot];
-                            if ((ew & 0xFFFF0000u) != tag) {            // no terminating newline in the staged region
-                                if (sub == 0 && byte0 + staged_len < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + slot_lo + slot));
-                                continue;                               // (else: unterminated last line, not an entry)
+                    if (MODE == 0) {
+                        // split: start and end of the wanted line are published independently;
+                        // lens[r] accumulates (end - start) mod 2^32 from two atomics.
+                        if (phase == want) {
+                            const int64_t r = q0 + ((base_phase + gi + 1u) >> ls);
+                            if ((size_t)r < a.max_rows) {
+                                const int64_t st = (int64_t)gp + 1 + a.start_offset;
+                                a.starts[r] = st;
+                                atomicSub((unsigned int *)&a.lens[r], (unsigned int)(uint64_t)st);
                             }
-                            L = (int)(ew & 0xFFFFu) - b0;
                         }
-                        if (sub == 0) {
-                            acc_bases += (uint64_t)L;
-                            atomicMax(&s_misc[1], (uint32_t)b0 + 1u);
-                            atomicMax(&s_misc[2], (uint32_t)(slot_lo + slot) + 1u);
+                        if (phase == fl) {
+                            const int64_t r = q0 + ((base_phase + gi) >> ls);
+                            if ((size_t)r < a.max_rows) {
+                                int64_t e = (int64_t)gp;
+                                if (cr && gp > 0 && a.chunk[gp - 1] == '\r') e -= 1;
+                                atomicAdd((unsigned int *)&a.lens[r], (unsigned int)(uint64_t)e);
+                            }
                         }
+                    }
+                }
+            }
+            // last complete entry of the tile proper: the last newline with phase pm
+            if (tid == 0 && tile_nl > 0) {
+                const uint32_t last = tile_nl - 1u;
+                const uint32_t back = (base_phase + last - pm) & pm;  // steps back to a phase-pm newline
+                if (last >= back) {
+                    const int li = (int)(last - back) - win_lo;
+                    if (li >= 0 && li < ev_hi)
+                        atomicMax((unsigned long long *)&a.status[BNPK_ST_N_COMPLETE_BYTES],
+                                  (unsigned long long)(byte0 + s_nlpos[li] + 1));
+                }
+            }
+            if (tile == 0 && tid == 0 && round == 0) {
+                if (a.n > 0 && a.chunk[0] != a.header_char)
+                    atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
+                if (MODE == 0 && fl == 0 && a.max_rows > 0) {       // the first line has no newline before it
+                    a.starts[0] = a.start_offset;
+                    atomicSub((unsigned int *)&a.lens[0], (unsigned int)a.start_offset);
+                }
+            }
+
+            // ---- 4. rows straight off the list: encode their units, then the k-mers -------------------
+            if (MODE == 1 && !(a.debug & 8)) {
+                // rows whose start newline index lies in this window
+                const int s_lo = (win_lo > (int)jr0) ? (int)((win_lo - jr0 + pm) >> ls) : 0;
+                int s_hi = n_rows_tile;
+                if (round != n_rounds - 1) s_hi = min(s_hi, (int)((win_lo + kNlStep - (int)jr0 + (int)pm) >> ls));
+                const uint64_t kmask = (1ull << (2 * a.k)) - 1;
+                const bool fast = ht.mask && ht.mask <= 0x3FFFFFFFull;
+                const uint32_t m32x4 = (uint32_t)(ht.mask & kmask) << 2;         // byte-offset mask into the table
+                constexpr int kGroups = MINIMIZER ? kCtaWarps : kCtaThreads / 4;  // rows handled concurrently
+                const int sub = MINIMIZER ? lane : (lane & 3);
+                const int nsub = MINIMIZER ? 32 : 4;
+                const int grp = MINIMIZER ? warp : (tid >> 2);
+                const unsigned gmask = MINIMIZER ? 0xffffffffu : (0xFu << (lane & ~3));
+                for (int slot0 = s_lo; slot0 < s_hi; slot0 += kGroups) {
+                    const int slot = slot0 + grp;
+                    if (slot >= s_hi) continue;
+                    const int li = (int)(jr0 + ((uint32_t)slot << ls)) - win_lo;   // list index of the row's start newline
+                    const int b0 = (int)s_nlpos[li] + 1 + a.start_offset;
+                    if ((uint32_t)(win_lo + li) + 1u >= all_nl) {   // no terminating newline in the staged region
+                        if (sub == 0 && byte0 + staged_len < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + slot));   // long row
+                        continue;                                    // (else: unterminated last line, not an entry)
+                    }
+                    int e = s_nlpos[li + 1];
+                    if (cr && e > b0 && a.chunk[byte0 + e - 1] == '\r') e -= 1;
+                    const int L = e - b0;
+                    if (sub == 0) {
+                        acc_bases += (uint64_t)L;
+                        atomicMax(&s_misc[1], (uint32_t)b0 + 1u);
+                        atomicMax(&s_misc[2], (uint32_t)slot + 1u);
+                    }
+                    // encode + validate the row's 16-byte units (re-read from L2); only sequence units are touched
+                    if (L > 0 && !(a.debug & 16)) {
+                        const int u1 = (e - 1) >> 4;
+                        for (int u = (b0 >> 4) + sub; u <= u1; u += nsub) {
+                            const uint4 q = load_unit_guarded(a.chunk, a.n, (int64_t)byte0 + 16 * (int64_t)u);
+                            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                            const int lo = max(b0 - 16 * u, 0), hi = min(e - 16 * u, 16);
+                            const uint32_t seq16 = (0xFFFFu >> (16 - hi)) & (0xFFFFu << lo);
+                            uint32_t bad;
+                            s_codes[u] = encode_unit_seq<ENC>(w, seq16, s_lut, bad);
+                            if (bad) {                                // rare: exact position, byte by byte
+                                for (int p = 16 * u + lo; p < 16 * u + hi; ++p) {
+                                    const uint32_t c = a.chunk[byte0 + p];
+                                    bool okb;
+                                    if (ENC == BNPK_ENC_CODES) okb = c < 4;
+                                    else if (ENC == BNPK_ENC_LUT) okb = s_lut[c] < 4;
+                                    else { const uint32_t uu = c | 0x20u; okb = (uu == 'a' || uu == 'c' || uu == 'g' || uu == 't'); }
+                                    if (!okb) {
+                                        atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE],
+                                                  (long long)(((r_first + slot) << 32) | (int64_t)(p - b0)));
+                                        break;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp(gmask);
+                    if constexpr (MINIMIZER) {
+                        if (L >= a.window) acc_values += row_count<SMEM_HIST, true>(s_codes, b0, L, a.k, a.window, ht, lane);
+                    } else {
                         const int npos = L - a.k + 1;
                         for (int p0 = sub * 32; p0 < npos; p0 += 128) {
                             const int n_here = min(32, npos - p0);
@@ -576,35 +552,20 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                                 const uint32_t w0 = s_codes[idx], w1 = s_codes[idx + 1], w2 = s_codes[idx + 2], w3 = s_codes[idx + 3];
                                 const uint32_t c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh), c2 = __funnelshift_r(w2, w3, sh);
                                 const uint32_t a0 = c0 << 2, a1 = __funnelshift_l(c0, c1, 2), a2 = __funnelshift_l(c1, c2, 2);
-                                if (n_here == 32) {
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32x4;
+                                for (int j = 0; j < 16; ++j) {
+                                    const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32x4;
+                                    if (j < n_here) {
                                         if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
                                         else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
                                     }
+                                }
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32x4;
+                                for (int j = 0; j < 16; ++j) {
+                                    const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32x4;
+                                    if (j + 16 < n_here) {
                                         if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
                                         else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32x4;
-                                        if (j < n_here) {
-                                            if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
-                                            else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
-                                        }
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) {
-                                        const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32x4;
-                                        if (j + 16 < n_here) {
-                                            if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
-                                            else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
-                                        }
                                     }
                                 }
                             } else {
@@ -613,71 +574,32 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                             }
                         }
                     }
-                } else {
-                    for (int slot = warp; slot < rows_here; slot += kCtaWarps) {
-                        int b0 = 0, L = 0;
-                        bool ok = false;
-                        if (lane == 0) ok = row_bounds(slot, b0, L);
-                        ok = __shfl_sync(0xffffffffu, ok, 0);
-                        b0 = __shfl_sync(0xffffffffu, b0, 0);
-                        L = __shfl_sync(0xffffffffu, L, 0);
-                        if (!ok) continue;
-                        if (lane == 0) {
-                            acc_bases += (uint64_t)L;
-                            atomicMax(&s_misc[1], (uint32_t)b0 + 1u);
-                            atomicMax(&s_misc[2], (uint32_t)(slot_lo + slot) + 1u);
-                        }
-                        if (L >= a.window) acc_values += row_count<SMEM_HIST, true>(s_codes, b0, L, a.k, a.window, ht, lane);
-                    }
-                }
-                // an invalid base was seen: find its (row, position) -- error path only
-                if (s_misc[4] != 0xFFFFFFFFu) {
-                    __syncthreads();
-                    if (warp == 0) {
-                        const int unit0 = (int)s_misc[4];
-                        for (int slot = lane; slot < rows_here; slot += 32) {
-                            const uint32_t ew = s_row_end[slot];
-                            if ((ew & 0xFFFF0000u) != tag) continue;
-                            const int b0 = s_row_start[slot], e = (int)(ew & 0xFFFFu);
-                            if (e <= unit0 || b0 >= unit0 + 16) continue;
-                            for (int p = max(b0, unit0); p < min(e, unit0 + 16); ++p) {
-                                const uint32_t c = a.chunk[byte0 + p];
-                                bool okb;
-                                if (ENC == BNPK_ENC_CODES) okb = c < 4;
-                                else if (ENC == BNPK_ENC_LUT) okb = s_lut[c] < 4;
-                                else { const uint32_t u = c | 0x20u; okb = (u == 'a' || u == 'c' || u == 'g' || u == 't'); }
-                                if (!okb) {
-                                    atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE],
-                                              (long long)(((r_first + slot_lo + slot) << 32) | (int64_t)(p - b0)));
-                                    break;
-                                }
-                            }
-                        }
-                    }
                 }
             }
         }
-        // ---- 6. front end of the new tile (its bytes were requested in step 4); rotate the pipeline ----
+        // ---- 5. front end of the new tile (its bytes were requested after S1); rotate the pipeline ------
         uint64_t nlN = 0;
-        uint32_t exN = 0, tnlN = 0;
+        uint32_t exN = 0, tnlN = 0, tallN = 0;
         if (tN < a.tile_end) {
-            front(tN, raw, nlN, exN, tnlN);                           // two __syncthreads inside
+            front(tN, raw, nlN, exN, tnlN, tallN);                   // two __syncthreads inside
         } else {
             __syncthreads();
         }
-        // per-tile global bookkeeping of the tile just finished (one atomic each; all its shared-memory
-        // atomics are ordered before the barrier(s) above)
+        // per-tile global bookkeeping of the tile just finished (its shared-memory atomics are ordered before
+        // the barrier(s) above)
         if (tid == 0) {
-            if (s_misc[0]) atomicMax((unsigned long long *)&a.status[BNPK_ST_N_COMPLETE_BYTES], (unsigned long long)(byte0 + s_misc[0]));
             if (MODE == 1 && s_misc[1]) {
+                const uint32_t base_phase = (uint32_t)line_base & pm;
+                const uint32_t jr0 = (want - base_phase) & pm;
+                const int64_t r_first = (line_base >> ls) + ((base_phase + jr0 + 1u) >> ls);
                 atomicMax((unsigned long long *)&a.status[BNPK_ST_LAST_ROW_START], (unsigned long long)(byte0 + s_misc[1] - 1) + 1ull);
                 atomicMax((unsigned long long *)&a.status[BNPK_ST_LAST_ROW_INDEX], (unsigned long long)(r_first + s_misc[2] - 1) + 1ull);
             }
             if (tile == a.n_tiles_total - 1) a.status[BNPK_ST_N_LINES] = line_base + tile_nl;
         }
-        tM = tP; nlM = nlP; exM = exP; tnlM = tnlP;
-        tP = tF; nlP = nlF; exP = exF; tnlP = tnlF;
-        tF = tN; nlF = nlN; exF = exN; tnlF = tnlN;
+        tM = tP; nlM = nlP; exM = exP; tnlM = tnlP; tallM = tallP;
+        tP = tF; nlP = nlF; exP = exF; tnlP = tnlF; tallP = tallF;
+        tF = tN; nlF = nlN; exF = exN; tnlF = tnlN; tallF = tallN;
     }
 
     // ---- flush ---------------------------------------------------------------------------------
