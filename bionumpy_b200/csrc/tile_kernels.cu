@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         int64_t next_ticket = 0;
         if (tid == 0) next_ticket = take_ticket();
         if (warp == 0) {
-            const uint64_t excl = lookback_finish(lb, tile, tile_nl, lane, lbA, lbB);
+            const uint64_t excl = (a.debug & 1) ? (uint64_t)tile * 208ull : lookback_finish(lb, tile, tile_nl, lane, lbA, lbB);
             if (lane == 0) {
                 s_line_base = (int64_t)excl;
                 s_misc[1] = 0; s_misc[2] = 0;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             {
                 uint64_t m = nlM;
                 int li = (int)exM - win_lo;
-                while (m) {
+                while (m && !(a.debug & 64)) {
                     const int bit = __ffsll((long long)m) - 1;
                     m &= m - 1;
                     if (li >= 0 && li < kNlCap) s_nlpos[li] = (uint16_t)(my0 + bit);
@@ -422,18 +422,18 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             const int ev_hi = (round == n_rounds - 1) ? n_in_win : kNlStep;
 
             // ---- 3. one thread per newline: validation, field publishing (split mode) -----------------
-            for (int i = tid; i < ev_hi; i += kCtaThreads) {
+            for (int i = tid; i < ev_hi && !(a.debug & 4); i += kCtaThreads) {
                 const uint32_t gi = (uint32_t)(win_lo + i);           // tile-relative newline index = rel line index
                 const int p = s_nlpos[i];
                 const size_t gp = byte0 + p;
                 const uint32_t phase = (base_phase + gi) & pm;
                 if (gi < tile_nl) {                                   // newline of the tile proper
-                    if (phase == pm) {                                // last line of an entry: next byte starts a header
+                    if (phase == pm && !(a.debug & 2)) {                                // last line of an entry: next byte starts a header
                         if (gp + 1 < a.n && a.chunk[gp + 1] != a.header_char)      // one_line_buffer.py:155-173
                             atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY],
                                       (long long)(q0 + ((base_phase + gi + 1u) >> ls)));
                     }
-                    if (a.check_plus && phase == 1u) {                             // fastq_buffer.py:38-45
+                    if (a.check_plus && phase == 1u && !(a.debug & 2)) {              // fastq_buffer.py:38-45
                         if (gp + 1 < a.n && a.chunk[gp + 1] != '+')
                             atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY],
                                       (long long)(q0 + ((base_phase + gi) >> ls)));
@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                 const uint64_t kmask = (1ull << (2 * a.k)) - 1;
                 const bool fast = ht.mask && ht.mask <= 0x3FFFFFFFull;
                 const uint32_t m32x4 = (uint32_t)(ht.mask & kmask) << 2;         // byte-offset mask into the table
+                const uint32_t need_bits = (uint32_t)__popcll(ht.mask & kmask);  // stream bits one table index needs
                 constexpr int kGroups = MINIMIZER ? kCtaWarps : kCtaThreads / 4;  // rows handled concurrently
                 const int sub = MINIMIZER ? lane : (lane & 3);
                 const int nsub = MINIMIZER ? 32 : 4;
@@ -549,7 +550,11 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                                 // stream pre-shifted left by 2 bits: (window & mask) is directly the byte offset
                                 const uint32_t bit = 2u * (uint32_t)(b0 + p0);
                                 const uint32_t idx = bit >> 5, sh = bit & 31u;
-                                const uint32_t w0 = s_codes[idx], w1 = s_codes[idx + 1], w2 = s_codes[idx + 2], w3 = s_codes[idx + 3];
+                                // read only words that hold bits of this row (neighbouring rows may still be
+                                // written by their own threads): last bit needed = last k-mer start + table bits
+                                const uint32_t last_w = (2u * (uint32_t)(b0 + p0 + n_here - 1) + need_bits - 1u) >> 5;
+                                const uint32_t w0 = s_codes[idx], w1 = idx + 1 <= last_w ? s_codes[idx + 1] : 0u;
+                                const uint32_t w2 = idx + 2 <= last_w ? s_codes[idx + 2] : 0u, w3 = idx + 3 <= last_w ? s_codes[idx + 3] : 0u;
                                 const uint32_t c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh), c2 = __funnelshift_r(w2, w3, sh);
                                 const uint32_t a0 = c0 << 2, a1 = __funnelshift_l(c0, c1, 2), a2 = __funnelshift_l(c1, c2, 2);
 #pragma unroll
