@@ -43,6 +43,7 @@ SIGNATURES = {
     "bnpk_row_offsets": (_i, [_vp, _sz, _i, _vp, _vp, _sz, _vp]),
     "bnpk_rows_encode": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp, _vp]),
     "bnpk_rows_kmer_hash": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "bnpk_rows_generic_hash": (_i, [_vp, _sz, _vp, _vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "bnpk_rows_minimizers": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "bnpk_rows_kmer_count": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
     "bnpk_bincount": (_i, [_vp, _sz, _i64, _i, _vp, _vp, _vp]),

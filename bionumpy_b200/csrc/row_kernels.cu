@@ -243,6 +243,41 @@ __global__ void uncount_kernel(const RowArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Generic alphabets (size != 4): h = sum_j code[i+j] * A^j in int64 arithmetic, the reference's
+// KmerEncoder dot product (sequence/kmers.py:17-27, sequence/rollable.py:49-66).  One warp per row,
+// one lane per window; codes come from a 256-byte LUT (or are the bytes themselves).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rows_generic_hash_kernel(const uint8_t *base, size_t base_bytes, const int64_t *starts,
+                                                                const int32_t *lens, size_t n_rows, const uint8_t *lut,
+                                                                int alphabet_size, int k, const int64_t *offsets,
+                                                                int64_t *out, int64_t *status) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ unsigned long long s_pow[64];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 256) s_lut[tid] = lut ? lut[tid] : (uint8_t)tid;
+    if (tid == 0) {
+        unsigned long long p = 1;
+        for (int j = 0; j < 64; ++j) { s_pow[j] = p; p *= (unsigned long long)alphabet_size; }
+    }
+    __syncthreads();
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + tid) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp_global; r < n_rows; r += n_warps) {
+        const int64_t start = starts[r], L = lens[r], o = offsets[r];
+        for (int64_t i = lane; i < L; i += 32) {                    // validity of every symbol of the row
+            const uint8_t c = s_lut[base[start + i]];
+            if (c >= alphabet_size) atomicMin((long long *)&status[BNPK_ST_BAD_BASE], (long long)(((int64_t)r << 32) | i));
+        }
+        for (int64_t i = lane; i + k <= L; i += 32) {
+            unsigned long long h = 0;
+            for (int j = 0; j < k; ++j) h += (unsigned long long)s_lut[base[start + i + j]] * s_pow[j];
+            out[o + i] = (int64_t)h;
+        }
+    }
+}
+
 static size_t rows_smem_bytes(bool counting, bool smem_hist, uint64_t n_bins) {
     size_t b = (size_t)kRowWarps * kWarpWords * 4 + 256;
     if (counting && smem_hist) b += n_bins * 4;
@@ -344,6 +379,20 @@ int bnpk_rows_kmer_hash(const uint8_t *base, size_t base_bytes, const int64_t *s
     a.base = base; a.base_bytes = base_bytes; a.starts = starts; a.lens = lens; a.n_rows = n_rows; a.lut = lut256;
     a.k = k; a.offsets = offsets; a.out = hashes_out; a.n_bins = 1; a.status = status;
     return launch_rows_enc<RM_HASH, false, false>(a, enc_mode, n_rows, (cudaStream_t)stream);
+}
+
+int bnpk_rows_generic_hash(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens, size_t n_rows,
+                            const uint8_t *lut256, int alphabet_size, int k, const int64_t *offsets, int64_t *hashes_out,
+                            int64_t *status, void *stream) {
+    if (k < 1 || k > 63) return set_err(BNPK_E_K, "k must be in 1..63 for the generic hash");
+    if (alphabet_size < 2 || alphabet_size > 255) return set_err(BNPK_E_BADARG, "alphabet_size must be in 2..255");
+    if (n_rows == 0) return 0;
+    const size_t want = (n_rows + 7) / 8;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(want, (size_t)sm_count() * 8));
+    rows_generic_hash_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(base, base_bytes, starts, lens, n_rows, lut256,
+                                                                    alphabet_size, k, offsets, hashes_out, status);
+    BNPK_LAUNCHED("rows_generic_hash_kernel");
+    return 0;
 }
 
 int bnpk_rows_minimizers(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens, size_t n_rows,

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             {
                 uint64_t m = nlM;
                 int li = (int)exM - win_lo;
-                while (m && !(a.debug & 64)) {
+                while (m) {
                     const int bit = __ffsll((long long)m) - 1;
                     m &= m - 1;
                     if (li >= 0 && li < kNlCap) s_nlpos[li] = (uint16_t)(my0 + bit);

@@ -147,6 +147,19 @@ def rows_kmer_hash(base, starts, lens, enc_mode, k, lut=None, offsets=None, stat
     return out, offsets, status
 
 
+def rows_generic_hash(base, starts, lens, alphabet_size, k, lut=None, offsets=None, status=None):
+    """sum_j code[i+j] * alphabet_size^j for alphabets that are not four letters (K3')."""
+    if offsets is None:
+        offsets = row_offsets(lens, k - 1)
+    total = int(offsets[-1].item())
+    out = torch.empty(total, dtype=torch.int64, device=base.device)
+    if status is None:
+        status = nv.new_status(base.device)
+    check(lib().bnpk_rows_generic_hash(*_rows_args(base, starts, lens), ptr(lut), alphabet_size, k, ptr(offsets),
+                                       ptr(out), ptr(status), stream_ptr()))
+    return out, offsets, status
+
+
 def rows_minimizers(base, starts, lens, enc_mode, k, window_size, lut=None, offsets=None, status=None, total=None):
     if offsets is None:
         offsets = row_offsets(lens, window_size - 1)

@@ -51,9 +51,6 @@ def _source_of(sequence) -> _Source:
     assert isinstance(enc, AlphabetEncoding), \
         "Sequence needs to be encoded with an AlphabetEncoding, e.g. DNAEncoding. " \
         "Change encoding of your sequences by using e.g. bnp.change_encoding(sequences, bnp.DNAEncoding)"
-    if enc.alphabet_size != 4:
-        raise NotImplementedError("only 4-letter alphabets are on the CUDA k-mer path "
-                                  "(the reference's generic dot-product path, kmers.py:87, is out of scope)")
     return _Source(data, starts, lens, nv.ENC_CODES, None, enc)
 
 
@@ -99,6 +96,14 @@ class LazyKmerValues(EncodedRaggedArray):
         if self._lazy is None:
             s = self._source
             shrink = (self._window if self._window else self._k) - 1
+            if s.alphabet_encoding.alphabet_size != 4:
+                # the reference's generic dot-product path (kmers.py:87): plain k-mers only
+                if self._window:
+                    raise NotImplementedError("minimizers are only implemented for 4-letter alphabets")
+                vals, _, status = ops.rows_generic_hash(s.base, s.starts, s.lens, s.alphabet_encoding.alphabet_size,
+                                                        self._k, None)
+                self._lazy = vals
+                return self._lazy
             offsets = ops.row_offsets(s.lens, shrink)
             p_starts, p_lens, p_off = _split_long_rows(s.starts, s.lens, shrink + 1, offsets)
             if p_off is not None and p_off is not offsets:
@@ -138,6 +143,9 @@ class LazyKmerValues(EncodedRaggedArray):
     def fused_histogram(self, n_bins: int) -> torch.Tensor:
         """hist[b] = #{values == b (mod n_bins)} without writing the values (K3/K4 + K5 fused)."""
         s = self._source
+        if s.alphabet_encoding.alphabet_size != 4:
+            hist, _ = ops.bincount(self._data.contiguous(), n_bins)
+            return hist
         buf = s.chunk_buffer
         if buf is not None and buf.can_fuse_count():
             return buf.fused_kmer_histogram(self._k, self._window, n_bins, s.enc_mode, s.lut)

@@ -162,6 +162,13 @@ int bnpk_rows_kmer_hash(const uint8_t *base, size_t base_bytes, const int64_t *s
                         int enc_mode, const uint8_t *lut256, int k, const int64_t *offsets,
                         int64_t *hashes_out, int64_t *status, void *stream);
 
+/* K3' the reference's generic path for alphabets whose size is not 4 (KmerEncoder dot product,
+ *     sequence/kmers.py:17-27,87): out[offsets[r] + i] = sum_j code[r][i+j] * alphabet_size^j in
+ *     int64 (wrapping) arithmetic.  lut256 maps bytes to codes (255 = invalid), NULL = bytes are codes. */
+int bnpk_rows_generic_hash(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens, size_t n_rows,
+                           const uint8_t *lut256, int alphabet_size, int k, const int64_t *offsets,
+                           int64_t *hashes_out, int64_t *status, void *stream);
+
 /* K4  get_minimizers (sequence/minimizers.py:20-54): out[offsets[r] + j] = min of the
  *     window_size-k+1 k-mer hashes of window j; offsets from shrink = window_size-1. */
 int bnpk_rows_minimizers(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens, size_t n_rows,

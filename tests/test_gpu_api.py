@@ -330,3 +330,23 @@ def test_genome_like_fasta_k21(bnp, tmp_path):
     assert np.array_equal(u_w, u_g) and np.array_equal(c_w, c_g)
     mins = bnp.get_minimizers(bnp.change_encoding(whole.sequence, bnp.DNAEncoding), 21, 31).raw().ravel().cpu().numpy()
     assert np.array_equal(mins, o.get_minimizers_fast(codes, np.array(lengths), 21, 31)[0])
+
+
+def test_generic_alphabet_kmers(bnp):
+    """tests/test_kmer.py:58-63 (AminoAcidEncoding branch) and the generic dot-product hash (kmers.py:17-27)."""
+    from oracle import bnp_oracle as o
+    seqs = bnp.as_encoded_array(["ACTG"], bnp.AminoAcidEncoding)
+    kmers = bnp.sequence.get_kmers(seqs, 1)
+    assert len(kmers[0]) == 4
+    rng = np.random.default_rng(2)
+    letters = bnp.AminoAcidEncoding.get_alphabet()
+    strings = ["".join(rng.choice(letters, size=int(rng.integers(0, 40)))) for _ in range(30)]
+    enc = bnp.as_encoded_array(strings, bnp.AminoAcidEncoding)
+    for k in (1, 3, 5):
+        got = bnp.get_kmers(enc, k)
+        codes = np.array([letters.index(c) for s in strings for c in s], dtype=np.uint8)
+        lens = np.array([len(s) for s in strings])
+        flat = o.generic_kmer_hashes_flat(codes, k, 21)
+        want, wl = o.ragged_drop_tail(flat, lens, k - 1) if k > 1 else (flat, lens)
+        assert np.array_equal(got.raw().ravel().cpu().numpy(), want) and got.lengths.cpu().tolist() == list(wl)
+    assert str(bnp.get_kmers(bnp.as_encoded_array(["MKV"], bnp.AminoAcidEncoding), 2)[0]) == "[MK, KV]"
