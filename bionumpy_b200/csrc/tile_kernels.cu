@@ -36,7 +36,6 @@ struct TileArgs {
     // count
     const uint8_t *lut;
     int k, window;                 // window = 0: k-mers; else minimizers over `window` bases
-    int debug;                     // BNPK_DEBUG env: timing experiments only (results become wrong)
     uint64_t n_bins;
     unsigned long long *hist;
 };
@@ -379,7 +378,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         int64_t next_ticket = 0;
         if (tid == 0) next_ticket = take_ticket();
         if (warp == 0) {
-            const uint64_t excl = (a.debug & 1) ? (uint64_t)tile * 208ull : lookback_finish(lb, tile, tile_nl, lane, lbA, lbB);
+            const uint64_t excl = lookback_finish(lb, tile, tile_nl, lane, lbA, lbB);
             if (lane == 0) {
                 s_line_base = (int64_t)excl;
                 s_misc[1] = 0; s_misc[2] = 0;
@@ -422,18 +421,18 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             const int ev_hi = (round == n_rounds - 1) ? n_in_win : kNlStep;
 
             // ---- 3. one thread per newline: validation, field publishing (split mode) -----------------
-            for (int i = tid; i < ev_hi && !(a.debug & 4); i += kCtaThreads) {
+            for (int i = tid; i < ev_hi; i += kCtaThreads) {
                 const uint32_t gi = (uint32_t)(win_lo + i);           // tile-relative newline index = rel line index
                 const int p = s_nlpos[i];
                 const size_t gp = byte0 + p;
                 const uint32_t phase = (base_phase + gi) & pm;
                 if (gi < tile_nl) {                                   // newline of the tile proper
-                    if (phase == pm && !(a.debug & 2)) {                                // last line of an entry: next byte starts a header
+                    if (phase == pm) {                                // last line of an entry: next byte starts a header
                         if (gp + 1 < a.n && a.chunk[gp + 1] != a.header_char)      // one_line_buffer.py:155-173
                             atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY],
                                       (long long)(q0 + ((base_phase + gi + 1u) >> ls)));
                     }
-                    if (a.check_plus && phase == 1u && !(a.debug & 2)) {              // fastq_buffer.py:38-45
+                    if (a.check_plus && phase == 1u) {              // fastq_buffer.py:38-45
                         if (gp + 1 < a.n && a.chunk[gp + 1] != '+')
                             atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY],
                                       (long long)(q0 + ((base_phase + gi) >> ls)));
@@ -481,7 +480,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             }
 
             // ---- 4. rows straight off the list: encode their units, then the k-mers -------------------
-            if (MODE == 1 && !(a.debug & 8)) {
+            if (MODE == 1) {
                 // rows whose start newline index lies in this window
                 const int s_lo = (win_lo > (int)jr0) ? (int)((win_lo - jr0 + pm) >> ls) : 0;
                 int s_hi = n_rows_tile;
@@ -513,7 +512,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                         atomicMax(&s_misc[2], (uint32_t)slot + 1u);
                     }
                     // encode + validate the row's 16-byte units (re-read from L2); only sequence units are touched
-                    if (L > 0 && !(a.debug & 16)) {
+                    if (L > 0) {
                         const int u1 = (e - 1) >> 4;
                         for (int u = (b0 >> 4) + sub; u <= u1; u += nsub) {
                             const uint4 q = load_unit_guarded(a.chunk, a.n, (int64_t)byte0 + 16 * (int64_t)u);
@@ -543,37 +542,47 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
                         if (L >= a.window) acc_values += row_count<SMEM_HIST, true>(s_codes, b0, L, a.k, a.window, ht, lane);
                     } else {
                         const int npos = L - a.k + 1;
-                        for (int p0 = sub * 32; p0 < npos; p0 += 128) {
-                            const int n_here = min(32, npos - p0);
-                            acc_values += (uint64_t)n_here;
-                            if (fast) {
-                                // stream pre-shifted left by 2 bits: (window & mask) is directly the byte offset
-                                const uint32_t bit = 2u * (uint32_t)(b0 + p0);
+                        if (fast) {
+                            // Interleaved positions: thread `sub` of the row's four takes p = sub + 4j, so the shift of
+                            // k-mer j inside its 32-bit stream word is 8*(j&3) + 2*sub: the 2*sub part is folded into a
+                            // per-thread rotated copy of the stream, what is left are constant byte shifts.  The stream
+                            // is also pre-shifted left by two bits so that (window & mask) is the table's byte offset.
+                            const uint32_t last_w = npos > 0 ? (2u * (uint32_t)(b0 + npos - 1) + need_bits - 1u) >> 5 : 0u;
+                            for (int pbase = 0; pbase < npos; pbase += 128) {
+                                const int nj = min((npos - pbase - sub + 3) >> 2, 32);      // my k-mers in this pass
+                                if (nj <= 0) continue;
+                                acc_values += (uint64_t)nj;
+                                const uint32_t bit = 2u * (uint32_t)(b0 + pbase);
                                 const uint32_t idx = bit >> 5, sh = bit & 31u;
-                                // read only words that hold bits of this row (neighbouring rows may still be
-                                // written by their own threads): last bit needed = last k-mer start + table bits
-                                const uint32_t last_w = (2u * (uint32_t)(b0 + p0 + n_here - 1) + need_bits - 1u) >> 5;
-                                const uint32_t w0 = s_codes[idx], w1 = idx + 1 <= last_w ? s_codes[idx + 1] : 0u;
-                                const uint32_t w2 = idx + 2 <= last_w ? s_codes[idx + 2] : 0u, w3 = idx + 3 <= last_w ? s_codes[idx + 3] : 0u;
-                                const uint32_t c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh), c2 = __funnelshift_r(w2, w3, sh);
-                                const uint32_t a0 = c0 << 2, a1 = __funnelshift_l(c0, c1, 2), a2 = __funnelshift_l(c1, c2, 2);
+                                // only words that hold bits of this row are read (neighbours may still be written)
+                                uint32_t wq = idx + 2 <= last_w ? s_codes[idx + 2] : 0u;
+                                const uint32_t wA = s_codes[idx], wB = idx + 1 <= last_w ? s_codes[idx + 1] : 0u;
+                                uint32_t c1 = __funnelshift_r(wB, wq, sh);
+                                uint32_t r0 = __funnelshift_r(__funnelshift_r(wA, wB, sh), c1, 2u * (uint32_t)sub);
+                                uint32_t rp0 = r0 << 2;
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const uint32_t v = __funnelshift_r(a0, a1, 2 * j) & m32x4;
-                                    if (j < n_here) {
-                                        if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
-                                        else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
-                                    }
-                                }
+                                for (int q = 0; q < 8; ++q) {
+                                    if (4 * q >= nj) break;
+                                    const uint32_t wn = idx + q + 3 <= last_w ? s_codes[idx + q + 3] : 0u;
+                                    const uint32_t c2 = __funnelshift_r(wq, wn, sh);
+                                    const uint32_t r1 = __funnelshift_r(c1, c2, 2u * (uint32_t)sub);
+                                    const uint32_t rp1 = __funnelshift_l(r0, r1, 2);
+                                    const int left = nj - 4 * q;
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const uint32_t v = __funnelshift_r(a1, a2, 2 * j) & m32x4;
-                                    if (j + 16 < n_here) {
-                                        if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
-                                        else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                    for (int t = 0; t < 4; ++t) {
+                                        const uint32_t v = __funnelshift_r(rp0, rp1, 8 * t) & m32x4;
+                                        if (t < left) {
+                                            if constexpr (SMEM_HIST) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s_hist) + v), 1u);
+                                            else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                        }
                                     }
+                                    wq = wn; c1 = c2; r0 = r1; rp0 = rp1;
                                 }
-                            } else {
+                            }
+                        } else {
+                            for (int p0 = sub * 32; p0 < npos; p0 += 128) {
+                                const int n_here = min(32, npos - p0);
+                                acc_values += (uint64_t)n_here;
                                 for (int j = 0; j < n_here; ++j)
                                     hist_add<SMEM_HIST>(ht, stream_64(s_codes, (uint32_t)(b0 + p0 + j)) & kmask);
                             }
@@ -637,9 +646,7 @@ static size_t tile_smem_bytes(int mode, uint64_t n_bins, bool smem_hist) {
 }
 
 template <int MODE, int ENC, bool SMEM_HIST, bool MINIMIZER>
-static int launch_tile(const TileArgs &a_in, cudaStream_t st) {
-    TileArgs a = a_in;
-    { const char *d = getenv("BNPK_DEBUG"); a.debug = d ? atoi(d) : 0; }
+static int launch_tile(const TileArgs &a, cudaStream_t st) {
     auto kern = tile_kernel<MODE, ENC, SMEM_HIST, MINIMIZER>;
     const size_t smem = tile_smem_bytes(MODE, a.n_bins, SMEM_HIST);
     static thread_local bool attr_done = false;  // per instantiation
