@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
     // front end of one tile: newline mask, block scan, publish the tile's newline count.
     // (two __syncthreads; must be called by every thread).  tnl = newlines of the tile proper,
     // tall = newlines of the whole staged region (tile + halo).
-    auto front = [&](int64_t tile, const uint32_t *raw, uint64_t &nl, uint32_t &ex, uint32_t &tnl, uint32_t &tall) {
+    auto front = [&](int64_t tile, const uint32_t *raw, uint64_t &nl, uint32_t &ex, int st_slot) {
         const int staged_len = staged_len_of(tile);
         nl = 0;
         if (my0 < staged_len) {
@@ -332,15 +332,13 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             const uint32_t tile_nl_w = __shfl_sync(0xffffffffu, winc, kMainThreads / 32 - 1);   // tile proper only
             const uint32_t all_nl_w = __shfl_sync(0xffffffffu, winc, kCtaWarps - 1);
             if (lane == 0) {
-                s_misc[3] = tile_nl_w;
-                s_misc[5] = all_nl_w;
+                s_misc[6 + 2 * st_slot] = tile_nl_w;                 // per-stage ring: newlines of the tile proper ...
+                s_misc[7 + 2 * st_slot] = all_nl_w;                  // ... and of the whole staged region
                 lookback_publish(lb, tile, tile_nl_w);
             }
         }
         __syncthreads();
         ex = s_warp[warp] + inc - cnt;
-        tnl = s_misc[3];
-        tall = s_misc[5];
     };
     auto take_ticket = [&]() -> int64_t {
         return a.tile_begin + (int64_t)atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
@@ -362,17 +360,18 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
     int64_t tM = s_tk[0], tP = s_tk[1], tF = s_tk[2];
     uint32_t raw[16];
     uint64_t nlM = 0, nlP = 0, nlF = 0, lbA = kFlagPrefix, lbB = kFlagPrefix;
-    uint32_t exM = 0, exP = 0, exF = 0, tnlM = 0, tnlP = 0, tnlF = 0, tallM = 0, tallP = 0, tallF = 0;
-    if (tM < a.tile_end) { load_raw(tM, raw); front(tM, raw, nlM, exM, tnlM, tallM); }
-    if (tP < a.tile_end) { load_raw(tP, raw); front(tP, raw, nlP, exP, tnlP, tallP); }
-    if (tF < a.tile_end) { load_raw(tF, raw); front(tF, raw, nlF, exF, tnlF, tallF); }
+    uint32_t exM = 0, exP = 0, exF = 0;
+    int slotM = 0;                                                  // ring slot of the main-stage tile (P: +1, F: +2 mod 3)
+    if (tM < a.tile_end) { load_raw(tM, raw); front(tM, raw, nlM, exM, 0); }
+    if (tP < a.tile_end) { load_raw(tP, raw); front(tP, raw, nlP, exP, 1); }
+    if (tF < a.tile_end) { load_raw(tF, raw); front(tF, raw, nlF, exF, 2); }
     if (warp == 0 && tM < a.tile_end) lookback_issue(lb, tM, lane, lbA, lbB);
 
     while (tM < a.tile_end) {
         const int64_t tile = tM;
         const size_t byte0 = (size_t)tile * kTileBytes;
         const int staged_len = staged_len_of(tile);
-        const uint32_t tile_nl = tnlM, all_nl = tallM;
+        const uint32_t tile_nl = s_misc[6 + 2 * slotM], all_nl = s_misc[7 + 2 * slotM];
 
         // ---- 1. resolve the prefix, ask for the next ticket ------------------------------------------
         int64_t next_ticket = 0;
@@ -593,9 +592,9 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
         }
         // ---- 5. front end of the new tile (its bytes were requested after S1); rotate the pipeline ------
         uint64_t nlN = 0;
-        uint32_t exN = 0, tnlN = 0, tallN = 0;
+        uint32_t exN = 0;
         if (tN < a.tile_end) {
-            front(tN, raw, nlN, exN, tnlN, tallN);                   // two __syncthreads inside
+            front(tN, raw, nlN, exN, slotM);                         // two __syncthreads inside; reuses the finished tile's slot
         } else {
             __syncthreads();
         }
@@ -611,9 +610,10 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             }
             if (tile == a.n_tiles_total - 1) a.status[BNPK_ST_N_LINES] = line_base + tile_nl;
         }
-        tM = tP; nlM = nlP; exM = exP; tnlM = tnlP; tallM = tallP;
-        tP = tF; nlP = nlF; exP = exF; tnlP = tnlF; tallP = tallF;
-        tF = tN; nlF = nlN; exF = exN; tnlF = tnlN; tallF = tallN;
+        tM = tP; nlM = nlP; exM = exP;
+        tP = tF; nlP = nlF; exP = exF;
+        tF = tN; nlF = nlN; exF = exN;
+        slotM = slotM == 2 ? 0 : slotM + 1;
     }
 
     // ---- flush ---------------------------------------------------------------------------------
