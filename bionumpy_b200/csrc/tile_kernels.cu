@@ -334,11 +334,13 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 0 ? 4 : 3) tile_kernel(co
             if (lane == 0) {
                 s_misc[6 + 2 * st_slot] = tile_nl_w;                 // per-stage ring: newlines of the tile proper ...
                 s_misc[7 + 2 * st_slot] = all_nl_w;                  // ... and of the whole staged region
-                lookback_publish(lb, tile, tile_nl_w);
             }
         }
         __syncthreads();
         ex = s_warp[warp] + inc - cnt;
+        // publish after the barrier: the round trip of its atomic (whose result only this thread needs) must not
+        // hold up the other warps
+        if (tid == 0) lookback_publish(lb, tile, s_misc[6 + 2 * st_slot]);
     };
     auto take_ticket = [&]() -> int64_t {
         return a.tile_begin + (int64_t)atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
