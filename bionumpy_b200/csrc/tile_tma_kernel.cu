@@ -36,20 +36,18 @@ constexpr int kMaxBins = 16384;
 constexpr uint32_t kNoCross = 0xFFFFFFFFu;
 static_assert(kGT == 256 && kGW == 8, "group geometry");
 
-// One contiguous block of shared memory per group (byte offsets from the group base)
-constexpr int kGoSlots = 0;                               // [kSlots][kSlot] staged bytes
-constexpr int kGoList = kGoSlots + kSlots * kSlot;        // u16 [2][kNlCap] sorted newline positions
-constexpr int kGoWsum = kGoList + 2 * kNlCap * 2;         // u32 [kSlots][8] warp totals of the newline counts
-constexpr int kGoCross = kGoWsum + kSlots * 8 * 4;        // u32 [kSlots (+1)] first newline of the halo, or kNoCross
-constexpr int kGoTk = kGoCross + 16;                      // u32 [2] ticket broadcast
-constexpr int kGoBase = kGoTk + 8;                        // i64 [2] line index of the tile's first byte
-constexpr int kGoBar = kGoBase + 16;                      // u64 [kSlots] mbarriers (+ pad)
-constexpr int kGroupBytes = kGoBar + 40;
-static_assert(kGroupBytes % 16 == 0 && kGoBase % 8 == 0 && kGoBar % 8 == 0, "group block alignment");
-// after the groups: byte masks for partial units, the 256-byte LUT
-constexpr int kOffMaskLo = kGroups * kGroupBytes;         // uint4 [17]: bytes >= lo
-constexpr int kOffMaskHi = kOffMaskLo + 17 * 16;          // uint4 [17]: bytes <  hi
-constexpr int kOffLut = kOffMaskHi + 17 * 16;
+// per-group control block (32-bit words)
+constexpr int kCtlWsum = 0;                     // [kSlots][8] warp totals of the newline counts
+constexpr int kCtlCross = 24;                   // [kSlots] first newline of the halo (slot-relative) or kNoCross
+constexpr int kCtlTk = 28;                      // [2] ticket broadcast
+constexpr int kCtlBase = 32;                    // int64 [2] line index of the tile's first byte
+constexpr int kCtlWords = 48;
+// shared memory after the histogram (bytes)
+constexpr int kOffSlots = 0;
+constexpr int kOffList = kOffSlots + kGroups * kSlots * kSlot;
+constexpr int kOffCtl = kOffList + kGroups * 2 * kNlCap * 2;
+constexpr int kOffBar = kOffCtl + kGroups * kCtlWords * 4;
+constexpr int kOffLut = kOffBar + ((kGroups * kSlots * 8 + 15) & ~15);
 constexpr int kFixedBytes = kOffLut + 256;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,49 +85,63 @@ __device__ __forceinline__ uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
     return d;
 }
+// one count into the CTA-private table (32-bit shared address)
+__device__ __forceinline__ void hist_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
+// ptxas never predicates ATOMS (it branches around it), so a masked count adds 0 or 1 instead
+__device__ __forceinline__ void hist_add_val(uint32_t addr, uint32_t val) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory"); }
+
 // Measured on B200 (tools/micro/pipe_bench.cu): LOP3/SHF/PRMT/IADD3 (ALU pipe) and IMAD (FMA pipe) each issue one
 // warp instruction every two cycles per SM sub-partition, a 50:50 mix reaches 0.65/clk and IMAD.HI only 0.23/clk.
 // This path is all integer work, so instruction count -- not bytes -- is what the kernel time follows.
-// one count into the CTA-private table (32-bit shared address).  ptxas never predicates ATOMS (it branches
-// around it), so a masked count adds 0 or 1 instead.
-__device__ __forceinline__ void hist_inc(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory"); }
-__device__ __forceinline__ void hist_add_val(uint32_t addr, uint32_t val) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory"); }
 
-// exact '\n' flags of a 16-byte unit, bit i = byte i.  Per word: zero-byte test of w ^ 0x0A.. (bit 7 of every
-// byte; bit 7 of the pattern is clear, so the last term can use w itself), one IMAD that lines the four flags
-// up in the top nibble of the product and one funnel shift that pushes them into the accumulator.
+// bit 7 of every byte that equals '\n' (bit 7 of the pattern is clear, so the last term can use w itself)
+__device__ __forceinline__ uint32_t newline_msb(uint32_t w) {
+    const uint32_t s = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(s | w) & 0x80808080u;
+}
+// exact '\n' flags of a 16-byte unit, bit i = byte i.  Per word: the zero-byte test, one IMAD that lines the four
+// flags up in the top nibble of the product and one funnel shift that pushes them into the accumulator.
 __device__ __forceinline__ uint32_t newline_mask16(const uint4 q) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t acc = 0;
 #pragma unroll
-    for (int j = 3; j >= 0; --j) {
-        const uint32_t s = ((w[j] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-        const uint32_t z = ~(s | w[j]) & 0x80808080u;
-        acc = __funnelshift_l(z * 0x00204081u, acc, 4);             // bits 28..31 of the product = flags of bytes 0..3
-    }
+    for (int j = 3; j >= 0; --j) acc = __funnelshift_l(newline_msb(w[j]) * 0x00204081u, acc, 4);
     return acc & 0xFFFFu;
 }
 
-// 16-byte unit -> 32 bits of 2-bit codes; `bad` != 0 iff a byte selected by the byte mask `bm` (0xFF per row byte)
-// is outside the alphabet (exact).  ASCII alphabets only; bytes outside the row are replaced by 'a' first.
+// 16-byte unit -> 32 bits of 2-bit codes (+ exact validation of the bytes selected by seq16).  Same result
+// as encode_unit_seq; the ASCII alphabets gather the four packed bytes with byte permutes.
 template <int ENC>
-__device__ __forceinline__ uint32_t encode_unit_ascii(const uint4 q, const uint4 bm, uint32_t &bad) {
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w}, m[4] = {bm.x, bm.y, bm.z, bm.w};
-    uint32_t dif[4], pk[4];
+__device__ __forceinline__ uint32_t encode_unit(const uint4 q, uint32_t seq16, const uint8_t *s_lut, uint32_t &bad) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    if constexpr (ENC == BNPK_ENC_ASCII_ACGT || ENC == BNPK_ENC_ASCII_ACTG) {
+        uint32_t dif[4], pk[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t v = (w[j] & m[j]) | (0x61616161u & ~m[j]);
-        uint32_t x;
-        if constexpr (ENC == BNPK_ENC_ASCII_ACGT) x = ((v >> 1) ^ (v >> 2)) & 0x03030303u;
-        else x = (v >> 1) & 0x03030303u;
-        pk[j] = x * 0x01041040u;                                   // top byte = the four codes, packed
-        const uint32_t y = x + (x >> 4);                           // disjoint bits: low byte = codes 0,1; byte 2 = codes 2,3
-        const uint32_t sel = prmt(y, 0u, 0x4420);                  // nibbles = the four codes
-        const uint32_t letters = (ENC == BNPK_ENC_ASCII_ACGT) ? 0x74676361u : 0x67746361u;  // "acgt" / "actg"
-        dif[j] = prmt(letters, 0u, sel) ^ (v | 0x20202020u);       // re-decode (PRMT as a 4-entry LUT) and compare
+        for (int j = 0; j < 4; ++j) {
+            uint32_t x;
+            if constexpr (ENC == BNPK_ENC_ASCII_ACGT) x = ((w[j] >> 1) ^ (w[j] >> 2)) & 0x03030303u;
+            else x = (w[j] >> 1) & 0x03030303u;
+            pk[j] = x * 0x01041040u;                               // top byte = the four codes, packed
+            const uint32_t y = x | (x >> 4);
+            const uint32_t sel = prmt(y, 0u, 0x4420);              // nibbles = the four codes
+            const uint32_t letters = (ENC == BNPK_ENC_ASCII_ACGT) ? 0x74676361u : 0x67746361u;  // "acgt" / "actg"
+            dif[j] = prmt(letters, 0u, sel) ^ (w[j] | 0x20202020u);
+        }
+        const uint32_t codes = prmt(prmt(pk[0], pk[1], 0x0073), prmt(pk[2], pk[3], 0x0073), 0x5410);
+        if (seq16 == 0xFFFFu) {
+            bad = dif[0] | dif[1] | dif[2] | dif[3];
+        } else {
+            bad = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t nz = (((dif[j] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dif[j]) & 0x80808080u;  // byte != 0
+                bad |= msb_to_nibble(nz) & (seq16 >> (4 * j)) & 0xFu;
+            }
+        }
+        return codes;
+    } else {
+        return encode_unit_seq<ENC>(w, seq16, s_lut, bad);
     }
-    bad = dif[0] | dif[1] | dif[2] | dif[3];
-    return prmt(prmt(pk[0], pk[1], 0x0073), prmt(pk[2], pk[3], 0x0073), 0x5410);
 }
 
 template <int ENC, bool SMEM_HIST>
@@ -138,65 +150,61 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem_raw);
     uint8_t *s_fixed = smem_raw + (SMEM_HIST ? ((a.n_bins * 4 + 127) & ~(uint64_t)127) : 0);
     const int tid = threadIdx.x, g = tid / kGT, gt = tid % kGT, lane = gt & 31, gw = gt >> 5;
-    uint8_t *gb = s_fixed + g * kGroupBytes;                        // everything of my group hangs off this
-    // The group's service warp (look-back, copies, tickets, scouting, halo scan) has no rows of its own.  Warp w
-    // runs on sub-partition w % 4, so the three groups take their service warp from three different sub-partitions.
-    const int svc = kGW - 1 - g;
-    const int row_rank = gw == svc ? kGW - 1 : (gw < svc ? gw : gw - 1);     // order in which warps take rows
-    const uint4 *s_mlo = reinterpret_cast<const uint4 *>(s_fixed + kOffMaskLo);
-    const uint4 *s_mhi = reinterpret_cast<const uint4 *>(s_fixed + kOffMaskHi);
+    uint8_t *g_slots = s_fixed + kOffSlots + g * (kSlots * kSlot);
+    uint16_t *g_list = reinterpret_cast<uint16_t *>(s_fixed + kOffList) + g * (2 * kNlCap);
+    uint32_t *g_ctl = reinterpret_cast<uint32_t *>(s_fixed + kOffCtl) + g * kCtlWords;
+    int64_t *g_base = reinterpret_cast<int64_t *>(g_ctl + kCtlBase);
+    const uint32_t g_bar = smem_addr(s_fixed + kOffBar) + g * (kSlots * 8);
     uint8_t *s_lut = s_fixed + kOffLut;
-    auto ctl32 = [&](int off) -> uint32_t & { return *reinterpret_cast<uint32_t *>(gb + off); };
 
     const LookbackArrays lb = lookback_arrays(a.ws, a.n_tiles_total);
     const bool cr = a.status[BNPK_ST_CR] != 0;
 
     if (ENC == BNPK_ENC_LUT && tid < 256) s_lut[tid] = a.lut[tid];
-    if (tid < 17 * 16) {                                            // byte masks: [lo][i] = i >= lo, [hi][i] = i < hi
-        const int e = tid >> 4, i = tid & 15;
-        s_fixed[kOffMaskLo + tid] = i >= e ? 0xFF : 0x00;
-        s_fixed[kOffMaskHi + tid] = i < e ? 0xFF : 0x00;
-    }
     if (SMEM_HIST)
         for (uint32_t b = tid; b < a.n_bins; b += kCta) s_hist[b] = 0;
     if (gt == 0) {
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) mbar_init(smem_addr(gb + kGoBar + 8 * s), 1);
+        for (int s = 0; s < kSlots; ++s) mbar_init(g_bar + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    uint32_t acc_bases = 0, acc_values = 0;                         // per thread: well inside 32 bits for any chunk
-    const uint32_t ls = (uint32_t)a.lpe_shift, pm = (1u << ls) - 1u;
-    const uint32_t want = ((uint32_t)a.field_line - 1u) & pm;
-    const int32_t tile_end = (int32_t)a.tile_end;
-    // loop invariants of the k-mer stage
-    const uint64_t hmask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
-    const uint64_t kmask = (1ull << (2 * a.k)) - 1;
-    const bool fast = hmask && hmask <= 0x3FFFFFFFull;              // the table index is a bit-field of the low 32 stream bits
-    const uint32_t m32x4 = (uint32_t)(hmask & kmask) << 2;          // byte-offset mask into the table
-    const uint32_t hist_sa = smem_addr(s_hist);
     HistTarget ht;
     ht.global = a.hist;
     ht.smem = s_hist;
     ht.n_bins = a.n_bins;
-    ht.mask = hmask;
+    ht.mask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
     ht.delta = 1ull;
+    const uint64_t kmask = (1ull << (2 * a.k)) - 1;
+    const bool fast = ht.mask && ht.mask <= 0x3FFFFFFFull;
+    const uint32_t m32x4 = (uint32_t)(ht.mask & kmask) << 2;       // byte-offset mask into the table
+    const uint32_t hist_sa = smem_addr(s_hist);
+    uint32_t acc_bases = 0, acc_values = 0;                         // per thread: well inside 32 bits for any chunk
+    const uint32_t ls = (uint32_t)a.lpe_shift, pm = (1u << ls) - 1u;
+    const uint32_t fl = (uint32_t)a.field_line;
+    const uint32_t want = (fl - 1u) & pm;
+    const int32_t tile_end = (int32_t)a.tile_end;
 
-    // conflict-free front-end read: load j fetches unit (j + rot) & 3 of my 64 bytes; halfword h of the
-    // byte-order mask comes from load (h - rot) & 3 (PRMT byte pair 0x10 + 0x22 * load)
+    // thread constants of the conflict-free front-end read: load j fetches unit (j + rot) & 3 of my 64 bytes
     const uint32_t rot = ((uint32_t)lane >> 1) & 3u;
-    const uint32_t sel_lo = (0x10u + 0x22u * ((0u - rot) & 3u)) | ((0x10u + 0x22u * ((1u - rot) & 3u)) << 8);
-    const uint32_t sel_hi = (0x10u + 0x22u * ((2u - rot) & 3u)) | ((0x10u + 0x22u * ((3u - rot) & 3u)) << 8);
+    uint32_t f_off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f_off[j] = 64u * (uint32_t)gt + 16u * (((uint32_t)j + rot) & 3u);
+    // halfword h of the byte-order mask comes from load (h - rot) & 3
+    uint32_t sel_lo = 0, sel_hi = 0;
+    {
+        // PRMT byte pair of load jj in (A = m0|m1<<16, B = m2|m3<<16) is 0x10 + 0x22*jj
+        sel_lo = (0x10u + 0x22u * ((0u - rot) & 3u)) | ((0x10u + 0x22u * ((1u - rot) & 3u)) << 8);
+        sel_hi = (0x10u + 0x22u * ((2u - rot) & 3u)) | ((0x10u + 0x22u * ((3u - rot) & 3u)) << 8);
+    }
     const uint32_t sub = (uint32_t)lane & 3u;
+    const int src1 = (lane & ~3) | (int)((sub + 1u) & 3u), src2 = (lane & ~3) | (int)((sub + 2u) & 3u),
+              src3 = (lane & ~3) | (int)((sub + 3u) & 3u);
 
-    // The first three tiles of every group are interleaved over the groups (tile j*G + group), so that the tiles
-    // in flight at any moment are consecutive across the grid; later tiles come from the ticket counter.
-    const int32_t n_groups = (int32_t)gridDim.x * kGroups, gid = (int32_t)blockIdx.x * kGroups + g;
-    const int32_t tile0 = (int32_t)a.tile_begin;
     auto take_ticket = [&]() -> int32_t {
-        const unsigned long long t = (unsigned long long)(tile0 + 3 * n_groups) + atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
-        return (int32_t)min(t, (unsigned long long)0x7FFFFFF0);
+        const unsigned long long t = (unsigned long long)a.tile_begin + atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
+        return (int32_t)min(t, (unsigned long long)0x7FFFFFFF);
     };
     auto staged_len_of = [&](int32_t tile) -> int {
         return (int)min((size_t)kSlot, a.n - (size_t)tile * kTileBytes);
@@ -204,10 +212,10 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
     auto issue_copy = [&](int32_t tile, int slot) {               // one thread
         const size_t byte0 = (size_t)tile * kTileBytes;
         const uint32_t bytes = (uint32_t)staged_len_of(tile) & ~15u;
-        const uint32_t bar = smem_addr(gb + kGoBar + 8 * slot);
+        const uint32_t bar = g_bar + 8 * slot;
         if (bytes) {
             mbar_expect_tx(bar, bytes);
-            bulk_g2s(smem_addr(gb + kGoSlots + slot * kSlot), a.chunk + byte0, bytes, bar);
+            bulk_g2s(smem_addr(g_slots + slot * kSlot), a.chunk + byte0, bytes, bar);
         } else {
             mbar_arrive(bar);
         }
@@ -223,17 +231,19 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
     };
     // front end of one tile (every thread of the group)
     auto front = [&](int32_t tile, int slot, uint32_t parity, uint64_t &nl, uint32_t &ex) {
-        uint8_t *sp = gb + kGoSlots + slot * kSlot;
+        const uint8_t *sp = g_slots + slot * kSlot;
         const int staged = staged_len_of(tile);
-        mbar_wait(smem_addr(gb + kGoBar + 8 * slot), parity);
+        mbar_wait(g_bar + 8 * slot, parity);
         if (staged & 15) {                                          // the chunk's last bytes: not a multiple of 16
             const int t0 = staged & ~15;
-            if (gt < (staged & 15)) sp[t0 + gt] = a.chunk[(size_t)tile * kTileBytes + t0 + gt];
+            if (gt < (staged & 15)) g_slots[slot * kSlot + t0 + gt] = a.chunk[(size_t)tile * kTileBytes + t0 + gt];
             group_bar(g);
         }
         uint32_t m[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = newline_mask16(lds128(sp + 64 * gt + 16 * ((j + (int)rot) & 3)));
+        for (int j = 0; j < 4; ++j) {
+            m[j] = newline_mask16(lds128(sp + f_off[j]));
+        }
         const uint32_t A = m[1] * 65536u + m[0], B = m[3] * 65536u + m[2];
         nl = ((uint64_t)prmt(A, B, sel_hi) << 32) | prmt(A, B, sel_lo);
         const int lim = min(staged, kTileBytes) - 64 * gt;          // my bytes inside the tile proper
@@ -246,90 +256,64 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
             if (lane >= o) inc += t;
         }
         ex = inc - cnt;
-        if (lane == 31) ctl32(kGoWsum + 4 * (8 * slot + gw)) = inc;
-        if (gw == svc) {                                           // first newline of the halo: end of the crossing row
+        if (lane == 31) g_ctl[kCtlWsum + 8 * slot + gw] = inc;
+        if (gw == kGW - 1) {                                        // first newline of the halo: end of the crossing row
             const int valid = min(max(staged - kTileBytes - 16 * lane, 0), 16);
             const uint32_t mm = newline_mask16(lds128(sp + kTileBytes + 16 * lane)) & ((1u << valid) - 1u);
             const unsigned b = __ballot_sync(0xffffffffu, mm != 0);
             const int srcl = b ? __ffs(b) - 1 : 0;
             const uint32_t pos = (uint32_t)(kTileBytes + 16 * lane + __ffs(mm) - 1);
             const uint32_t first = __shfl_sync(0xffffffffu, pos, srcl);
-            if (lane == 0) ctl32(kGoCross + 4 * slot) = b ? first : kNoCross;
+            if (lane == 0) g_ctl[kCtlCross + slot] = b ? first : kNoCross;
         }
-    };
-    // One warp: exact number of newlines of a tile, read straight from global memory (the tile is copied into a slot
-    // only an iteration or two later and then hits L2).  Its count is published as soon as the ticket is known, so
-    // every successor finds it long before it needs it: the look-back never waits on a neighbour's pipeline.
-    auto scout_publish = [&](int32_t tile) {
-        const size_t byte0 = (size_t)tile * kTileBytes;
-        const int len = (int)min((size_t)kTileBytes, a.n - byte0);
-        const uint4 *p = reinterpret_cast<const uint4 *>(a.chunk + byte0);
-        const int n_units = len >> 4;
-        uint32_t acc = 0;                                           // 128 per newline (bit 7 of the matching byte)
-        for (int u0 = 0; u0 < n_units; u0 += 32 * 8) {
-            uint4 q[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int u = u0 + 32 * j + lane;
-                q[j] = u < n_units ? ld_stream(p + u) : make_uint4(0u, 0u, 0u, 0u);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t t = ((w[i] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-                    acc = __dp4a(~(t | w[i]) & 0x80808080u, 0x01010101u, acc);
-                }
-            }
-        }
-        if (lane < (len & 15)) acc += a.chunk[byte0 + (size_t)(len & ~15) + lane] == '\n' ? 128u : 0u;
-        const uint32_t cnt = __reduce_add_sync(0xffffffffu, acc) >> 7;
-        if (lane == 0) lookback_publish(lb, tile, cnt);
-    };
-    // One warp: exclusive line prefix of a tile whose count is already published -> shared
-    auto resolve = [&](int32_t tile, int slot, int base_buf) {
-        const uint32_t v = lane < kGW ? ctl32(kGoWsum + 4 * (8 * slot + lane)) : 0u;
-        const uint32_t cnt = __reduce_add_sync(0xffffffffu, v);
-        uint64_t lbA, lbB;
-        lookback_issue(lb, tile, lane, lbA, lbB);
-        const uint64_t excl = lookback_finish(lb, tile, cnt, lane, lbA, lbB);
-        if (lane == 0) *reinterpret_cast<int64_t *>(gb + kGoBase + 8 * base_buf) = (int64_t)excl;
     };
 
     // ---- prologue ---------------------------------------------------------------------------------------
-    int32_t tM = tile0 + gid, tP = min(tile0 + n_groups + gid, 0x7FFFFFF0), tF = min(tile0 + 2 * n_groups + gid, 0x7FFFFFF0);
-    if (gw < 3) {
-        const int32_t t = gw == 0 ? tM : (gw == 1 ? tP : tF);
-        if (t < tile_end) scout_publish(t);
+    int32_t tF = 0, t_next = 0;                                     // lane 0 of warp 0 only
+    if (gt == 0) {
+        const int32_t t0 = take_ticket(), t1 = take_ticket();
+        tF = take_ticket();
+        g_ctl[kCtlTk + 0] = (uint32_t)t0;
+        g_ctl[kCtlTk + 1] = (uint32_t)t1;
+        if (t0 < tile_end) issue_copy(t0, 0);
+        if (t1 < tile_end) issue_copy(t1, 1);
     }
-    if (gt == svc * 32) {
-        if (tM < tile_end) issue_copy(tM, 0);
-        if (tP < tile_end) issue_copy(tP, 1);
-    }
-    uint64_t nlM = 0;
+    group_bar(g);
+    int32_t tM = (int32_t)g_ctl[kCtlTk + 0], tP = (int32_t)g_ctl[kCtlTk + 1];
+    uint64_t nlM = 0, lbA = kFlagPrefix, lbB = kFlagPrefix;
     uint32_t exM = 0;
     if (tM < tile_end) front(tM, 0, 0u, nlM, exM);
-    group_bar(g);                                                   // warp totals of M visible
-    if (gw == svc && tM < tile_end) resolve(tM, 0, 0);
+    group_bar(g);                                                   // warp totals of M visible; ticket words free
+    if (gw == 0 && tM < tile_end) {
+        const uint32_t v = lane < kGW ? g_ctl[kCtlWsum + lane] : 0u;
+        const uint32_t cntM = __reduce_add_sync(0xffffffffu, v);
+        if (lane == 0) lookback_publish(lb, tM, cntM);
+        lookback_issue(lb, tM, lane, lbA, lbB);
+        const uint64_t excl = lookback_finish(lb, tM, cntM, lane, lbA, lbB);
+        if (lane == 0) g_base[0] = (int64_t)excl;
+    }
     int slotM = 0, slotP = 1;
     uint32_t parP = 0;
     uint32_t mb = 0;                                                // iteration parity: list / base / ticket buffers
 
     while (tM < tile_end) {
         const bool hasP = tP < tile_end;
+        const int slotF = slotM == 0 ? 2 : slotM - 1;               // the slot the previous tile just left
         // ---- a. front end of the pending tile ----------------------------------------------------------
         uint64_t nlP = 0;
         uint32_t exP = 0;
         if (hasP) front(tP, slotP, parP, nlP, exP);
         // ---- b. sorted newline list of the main tile (window 0) ----------------------------------------
+        const uint8_t *sp = g_slots + slotM * kSlot;
+        const size_t byte0 = (size_t)tM * kTileBytes;
+        const int staged = staged_len_of(tM);
         uint32_t tile_nl, my_excl;
         {
-            const uint32_t v = lane < kGW ? ctl32(kGoWsum + 4 * (8 * slotM + lane)) : 0u;
+            const uint32_t v = lane < kGW ? g_ctl[kCtlWsum + 8 * slotM + lane] : 0u;
             tile_nl = __reduce_add_sync(0xffffffffu, v);
             my_excl = exM + __reduce_add_sync(0xffffffffu, lane < gw ? v : 0u);
         }
-        uint16_t *list = reinterpret_cast<uint16_t *>(gb + kGoList) + mb * kNlCap;
+        uint16_t *list = g_list + mb * kNlCap;
         {
             uint64_t m = nlM;
             uint32_t li = my_excl;
@@ -340,32 +324,35 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                 ++li;
             }
         }
-        if (gt == svc * 32) ctl32(kGoTk + 4 * mb) = (uint32_t)tF;
+        if (gt == 0) g_ctl[kCtlTk + mb] = (uint32_t)tF;
         group_bar(g);                                               // ---- the barrier ----
-        // ---- c. service warp: refill the slot the previous tile left, resolve P, scout the next ticket -------
-        if (gw == svc) {
-            int32_t t_new = 0x7FFFFFF0;
-            if (lane == 0 && tF < tile_end) {
-                issue_copy(tF, slotM == 0 ? kSlots - 1 : slotM - 1);
-                t_new = take_ticket();
+        // ---- c. publish P, refill the free slot, next ticket, P's look-back loads ------------------------
+        uint32_t cntP = 0;
+        if (gw == 0) {
+            if (hasP) {
+                const uint32_t v = lane < kGW ? g_ctl[kCtlWsum + 8 * slotP + lane] : 0u;
+                cntP = __reduce_add_sync(0xffffffffu, v);
             }
-            if (hasP) resolve(tP, slotP, (int)(mb ^ 1u));
-            t_new = __shfl_sync(0xffffffffu, t_new, 0);
-            if (t_new < tile_end) scout_publish(t_new);
-            tF = t_new;
+            if (lane == 0) {
+                if (hasP) lookback_publish(lb, tP, cntP);
+                if (tF < tile_end) {
+                    issue_copy(tF, slotF);
+                    t_next = take_ticket();
+                } else {
+                    t_next = tF;
+                }
+            }
+            if (hasP) lookback_issue(lb, tP, lane, lbA, lbB);
         }
         // ---- d. the main tile -------------------------------------------------------------------------
-        const uint8_t *sp = gb + kGoSlots + slotM * kSlot;
-        const size_t byte0 = (size_t)tM * kTileBytes;
-        const int64_t line_base = *reinterpret_cast<const int64_t *>(gb + kGoBase + 8 * mb);
-        const uint32_t crossM = ctl32(kGoCross + 4 * slotM);
+        const int64_t line_base = g_base[mb];
+        const uint32_t crossM = g_ctl[kCtlCross + slotM];
         const uint32_t base_phase = (uint32_t)line_base & pm;
         const int64_t q0 = line_base >> ls;                         // entry index of the tile's first line
         const uint32_t jr0 = (want - base_phase) & pm;              // first newline (rel) that precedes a field line
         const int64_t r_first = q0 + ((base_phase + jr0 + 1u) >> ls);
         const int n_rows_tile = (tile_nl > jr0) ? (int)(((tile_nl - 1u - jr0) >> ls) + 1u) : 0;
-        int n_rounds = 1;
-        if (tile_nl > (uint32_t)kNlCap) n_rounds = (int)((tile_nl - 8u + kNlStep - 1) / kNlStep);
+        const int n_rounds = tile_nl > (uint32_t)kNlCap ? (int)((tile_nl - 8u + kNlStep - 1) / kNlStep) : 1;
         for (int round = 0; round < n_rounds; ++round) {
             const int win_lo = round * kNlStep;
             if (round > 0) {                                        // rare: more than kNlCap lines in one tile
@@ -396,25 +383,24 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                         atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY], (long long)(q0 + ((base_phase + gi) >> ls)));
                 }
             }
-            if (gt == 0) {
-                if (tile_nl > 0) {                                  // last complete entry of the tile
-                    const uint32_t last = tile_nl - 1u;
-                    const uint32_t back = (base_phase + last - pm) & pm;
-                    if (last >= back) {
-                        const int li = (int)(last - back) - win_lo;
-                        if (li >= 0 && li < ev_hi)
-                            atomicMax((unsigned long long *)&a.status[BNPK_ST_N_COMPLETE_BYTES], (unsigned long long)(byte0 + list[li] + 1));
-                    }
+            if (gt == 0 && tile_nl > 0) {                           // last complete entry of the tile
+                const uint32_t last = tile_nl - 1u;
+                const uint32_t back = (base_phase + last - pm) & pm;
+                if (last >= back) {
+                    const int li = (int)(last - back) - win_lo;
+                    if (li >= 0 && li < ev_hi)
+                        atomicMax((unsigned long long *)&a.status[BNPK_ST_N_COMPLETE_BYTES], (unsigned long long)(byte0 + list[li] + 1));
                 }
-                if (tM == 0 && round == 0 && a.n > 0 && sp[0] != a.header_char)
-                    atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
+            }
+            if (tM == 0 && gt == 0 && round == 0) {
+                if (a.n > 0 && sp[0] != a.header_char) atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
             }
             // rows whose start newline lies in this window: four threads per row
             const int s_lo = (win_lo > (int)jr0) ? (int)((win_lo - jr0 + pm) >> ls) : 0;
             int s_hi = n_rows_tile;
             if (round != n_rounds - 1) s_hi = min(s_hi, (int)((win_lo + kNlStep - (int)jr0 + (int)pm) >> ls));
             for (int s0 = s_lo; s0 < s_hi; s0 += kGT / 4) {
-                const int s = s0 + 8 * row_rank + (lane >> 2);
+                const int s = s0 + (gt >> 2);
                 bool act = s < s_hi;
                 int b0 = 0, e = 0;
                 if (act) {
@@ -425,7 +411,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                     } else if (crossM != kNoCross) {
                         e = (int)crossM;
                     } else {                                        // not terminated inside the slot
-                        if (sub == 0 && byte0 + (size_t)staged_len_of(tM) < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + s));
+                        if (sub == 0 && byte0 + staged < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + s));
                         act = false;                                // (else: unterminated last line, not an entry)
                     }
                     if (act && cr && e > b0 && sp[e - 1] == '\r') e -= 1;
@@ -453,14 +439,9 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                     if (L <= 0 || u > A1) return 0u;
                     const uint4 q = lds128(sp + 16 * u);
                     const int lo = max(b0 - 16 * u, 0), hi = min(e - 16 * u, 16);
-                    uint32_t bad, codes;
-                    if constexpr (ENC == BNPK_ENC_ASCII_ACGT || ENC == BNPK_ENC_ASCII_ACTG) {
-                        const uint4 ml = s_mlo[lo], mh = s_mhi[hi];
-                        codes = encode_unit_ascii<ENC>(q, make_uint4(ml.x & mh.x, ml.y & mh.y, ml.z & mh.z, ml.w & mh.w), bad);
-                    } else {
-                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                        codes = encode_unit_seq<ENC>(w, (0xFFFFu >> (16 - hi)) & (0xFFFFu << lo), s_lut, bad);
-                    }
+                    const uint32_t seq16 = (0xFFFFu >> (16 - hi)) & (0xFFFFu << lo);
+                    uint32_t bad;
+                    const uint32_t codes = encode_unit<ENC>(q, seq16, s_lut, bad);
                     if (bad) {                                      // rare: exact position, byte by byte
                         for (int p = 16 * u + lo; p < 16 * u + hi; ++p) {
                             const uint32_t c = sp[p];
@@ -476,11 +457,10 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                     }
                     return codes;
                 };
-                // code words of the following aligned units of my row: lanes of my quad, this round or the next
-                const int src1 = (lane & ~3) | (int)((sub + 1u) & 3u), src2 = (lane & ~3) | (int)((sub + 2u) & 3u);
                 uint32_t c_cur = enc(0);
                 for (int r = 0; r < R; ++r) {
                     const uint32_t c_nxt = enc(r + 1);
+                    // code words of the next aligned units of my row: lanes of my quad, this round or the next
                     const uint32_t x1 = __shfl_sync(0xffffffffu, c_cur, src1), y1 = __shfl_sync(0xffffffffu, c_nxt, src1);
                     const uint32_t x2 = __shfl_sync(0xffffffffu, c_cur, src2), y2 = __shfl_sync(0xffffffffu, c_nxt, src2);
                     const uint32_t w1 = sub + 1u >= 4u ? y1 : x1, w2 = sub + 2u >= 4u ? y2 : x2;
@@ -511,7 +491,6 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                             }
                         }
                     } else {
-                        const int src3 = (lane & ~3) | (int)((sub + 3u) & 3u);
                         const uint32_t x3 = __shfl_sync(0xffffffffu, c_cur, src3), y3 = __shfl_sync(0xffffffffu, c_nxt, src3);
                         const uint32_t w3 = sub + 3u >= 4u ? y3 : x3;
                         if (left > 0) {
@@ -532,9 +511,14 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
             }
         }
         if (tM == (int32_t)(a.n_tiles_total - 1) && gt == 0) a.status[BNPK_ST_N_LINES] = line_base + tile_nl;
-        // ---- e. rotate ---------------------------------------------------------------------------------
+        // ---- e. the pending tile's line prefix; rotate ---------------------------------------------------
+        if (gw == 0 && hasP) {
+            const uint64_t excl = lookback_finish(lb, tP, cntP, lane, lbA, lbB);
+            if (lane == 0) g_base[mb ^ 1u] = (int64_t)excl;
+        }
         tM = tP; nlM = nlP; exM = exP;
-        tP = (int32_t)ctl32(kGoTk + 4 * mb);
+        tP = (int32_t)g_ctl[kCtlTk + mb];
+        if (gt == 0) tF = t_next;
         slotM = slotP;
         slotP = slotP == kSlots - 1 ? 0 : slotP + 1;
         if (slotP == 0) parP ^= 1u;
@@ -549,7 +533,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
             if (c) atomicAdd(a.hist + b, (unsigned long long)c);
         }
     }
-    uint64_t sum_bases = warp_sum_u64(acc_bases), sum_values = warp_sum_u64(acc_values);
+    const uint64_t sum_bases = warp_sum_u64(acc_bases), sum_values = warp_sum_u64(acc_values);
     if (lane == 0) {
         if (sum_bases) atomicAdd((unsigned long long *)&a.status[BNPK_ST_N_BASES], sum_bases);
         if (sum_values) atomicAdd((unsigned long long *)&a.status[BNPK_ST_N_VALUES], sum_values);
@@ -586,7 +570,7 @@ bool tma_count_eligible(const TileArgs &a, bool smem_hist) {
     if (a.window != 0) return false;                                        // minimizers: register-staged kernel
     if ((reinterpret_cast<uintptr_t>(a.chunk) & 15) != 0) return false;     // bulk copies need 16-byte alignment
     if (smem_hist && a.n_bins > (uint64_t)tma::kMaxBins) return false;
-    if (a.tile_end > 0x7FFF0000ll) return false;
+    if (a.tile_end > 0x7FFFFFF0ll) return false;
     return true;
 }
 

@@ -128,6 +128,38 @@ def test_chunk_count_random_ragged(ops, seed, n, min_len, max_len, cr, lower, k,
         assert np.array_equal(hist.cpu().numpy(), want), cut
 
 
+def test_chunk_count_dense_newlines(ops):
+    """Records of 8-10 bytes: hundreds of newlines per 2 KiB, far beyond the per-warp newline list (windows)."""
+    rng = np.random.default_rng(21)
+    parts = []
+    for _ in range(30000):
+        L = int(rng.integers(0, 4))
+        seq = "".join(rng.choice(list("ACGT"), size=L)) if L else ""
+        parts.append(f"@\n{seq}\n+\n{'I' * L}\n")
+    chunk = np.frombuffer("".join(parts).encode("ascii"), dtype=np.uint8).copy()
+    for k, bins in ((1, 4), (2, 16), (3, 1 << 14)):
+        want, size, n_bases = oracle_hist(chunk, k, bins)
+        hist, status = ops.chunk_kmer_count(dev(chunk), k, bins)
+        st = ops.read_status(status)
+        assert (st.n_records, st.n_complete_bytes, st.n_bases) == (30000, size, n_bases)
+        assert np.array_equal(hist.cpu().numpy(), want)
+
+
+def test_chunk_count_unaligned_chunk_pointer(ops):
+    """A chunk that does not start on a 16-byte boundary takes the register-staged kernel (no bulk copies)."""
+    n = 20000
+    buf = torch.empty(n * 317 + 64, dtype=torch.uint8, device="cuda")
+    host = o.synthetic_fastq(0, n)
+    want, size, n_bases = oracle_hist(host, 31, 1 << 14)
+    for shift in (0, 1, 7, 16, 33):
+        view = buf[shift: shift + n * 317]
+        view.copy_(dev(host))
+        hist, status = ops.chunk_kmer_count(view, 31, 1 << 14)
+        st = ops.read_status(status)
+        assert (st.n_records, st.n_complete_bytes, st.n_bases) == (n, size, n_bases), shift
+        assert np.array_equal(hist.cpu().numpy(), want), shift
+
+
 def test_chunk_count_incomplete_tail_lines(ops):
     """Every possible cut of the last record: the sequence line of an incomplete entry must not count."""
     rng = np.random.default_rng(5)
