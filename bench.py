@@ -270,14 +270,14 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = world * n * READ_LEN / (ms_per_step * 1e-3) / 1e9
 
-    # roofline of the dominant kernel (tile_kernel): algorithmic bytes per launch / event-timed duration
+    # roofline of the dominant kernel (tile_tma_kernel): algorithmic bytes per launch / event-timed duration
     alg_bytes = n_bytes + 16 * n + 8 * args.buckets       # chunk once + row vector + histogram
     kern_ms = tot_ms.value / max(n_l.value, 1)
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic_from_profiles("tile_kernel_dram_bytes_per_10M_reads"),
-                "kernel": "bnpk::tile_kernel (fused split+encode+hash+count)", "kernel_ms": round(kern_ms, 4),
+                "kernel": "bnpk::tma::tile_tma_kernel (fused split+encode+hash+count, shared-memory staged)", "kernel_ms": round(kern_ms, 4),
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": round(kern_ms / ms_per_step, 3)}
 
