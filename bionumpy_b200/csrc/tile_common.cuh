@@ -27,6 +27,7 @@ struct TileArgs {
     int k, window;                 // window = 0: k-mers; else minimizers over `window` bases
     uint64_t n_bins;
     unsigned long long *hist;
+    uint32_t *hist32;              // optional 32-bit scratch table in the workspace (large global tables), else null
 };
 
 // 256-bit streaming load (sm_100: LDG.E.256), read-only path, no L1 allocation
@@ -186,6 +187,7 @@ __device__ __forceinline__ uint64_t lookback_finish(const LookbackArrays &l, int
 // the shared-memory-staged fused count (tile_tma_kernel.cu).  Returns -1 when the launch does not
 // qualify (minimizers, unaligned chunk, too many bins for its table) and the caller must fall back.
 bool tma_count_eligible(const TileArgs &a, bool smem_hist);
+constexpr int64_t kScratch32MaxBins = 1ll << 24;   // 64 MiB of u32 counters at the end of the workspace
 int launch_tma_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st);
 
 }  // namespace bnpk

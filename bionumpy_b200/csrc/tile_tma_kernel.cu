@@ -144,8 +144,10 @@ __device__ __forceinline__ uint32_t encode_unit(const uint4 q, uint32_t seq16, c
     }
 }
 
-template <int ENC, bool SMEM_HIST>
+// HIST: 0 = global int64 table, 1 = CTA-private u32 table in shared memory, 2 = global u32 scratch table
+template <int ENC, int HIST>
 __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
+    constexpr bool SMEM_HIST = HIST == 1;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem_raw);
     uint8_t *s_fixed = smem_raw + (SMEM_HIST ? ((a.n_bins * 4 + 127) & ~(uint64_t)127) : 0);
@@ -486,7 +488,10 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
 #pragma unroll
                                 for (int t = 0; t < 16; ++t) {
                                     const uint32_t v = (t == 0 ? a0 : __funnelshift_r(a0, a1, 2 * t)) & m32x4;
-                                    if (t < left) atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                    if (t < left) {
+                                        if constexpr (HIST == 2) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(a.hist32) + v), 1u);
+                                        else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                    }
                                 }
                             }
                         }
@@ -501,7 +506,9 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                             for (int t = 0; t < 16; ++t) {
                                 if (t < left) {
                                     const uint32_t lo32 = __funnelshift_r(a0, a1, 2 * t), hi32 = __funnelshift_r(a1, a2, 2 * t);
-                                    hist_add<SMEM_HIST>(ht, (((uint64_t)hi32 << 32) | lo32) & kmask);
+                                    const uint64_t h = (((uint64_t)hi32 << 32) | lo32) & kmask;
+                                    if constexpr (HIST == 2) atomicAdd(a.hist32 + (ht.mask ? (h & ht.mask) : (h % ht.n_bins)), 1u);
+                                    else hist_add<SMEM_HIST>(ht, h);
                                 }
                             }
                         }
@@ -540,10 +547,10 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
     }
 }
 
-template <int ENC, bool SMEM_HIST>
+template <int ENC, int HIST>
 static int launch_t(const TileArgs &a, cudaStream_t st) {
-    auto kern = tile_tma_kernel<ENC, SMEM_HIST>;
-    const size_t smem = (size_t)kFixedBytes + (SMEM_HIST ? ((a.n_bins * 4 + 127) & ~(uint64_t)127) : 0);
+    auto kern = tile_tma_kernel<ENC, HIST>;
+    const size_t smem = (size_t)kFixedBytes + (HIST == 1 ? ((a.n_bins * 4 + 127) & ~(uint64_t)127) : 0);
     static thread_local bool attr_done = false;  // per instantiation
     if (!attr_done) {
         BNPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFixedBytes + kMaxBins * 4));
@@ -561,7 +568,8 @@ static int launch_t(const TileArgs &a, cudaStream_t st) {
 
 template <int ENC>
 static int launch_enc(const TileArgs &a, bool smem_hist, cudaStream_t st) {
-    return smem_hist ? launch_t<ENC, true>(a, st) : launch_t<ENC, false>(a, st);
+    if (smem_hist) return launch_t<ENC, 1>(a, st);
+    return a.hist32 ? launch_t<ENC, 2>(a, st) : launch_t<ENC, 0>(a, st);
 }
 
 }  // namespace tma
