@@ -106,8 +106,10 @@ int bnpk_count_byte(const uint8_t *chunk, size_t n, uint8_t value, int64_t *coun
  *                    0 = never, 1 = always
  *   starts/lens      out, capacity `max_rows` rows (extra rows are counted, not written)
  *   status           device int64[BNPK_ST_WORDS], pre-initialised
- *   workspace        device scratch of bnpk_tile_workspace_bytes(n) bytes, zero it with
- *                    bnpk_tile_workspace_reset before each independent chunk
+ *   workspace        device scratch of bnpk_tile_workspace_bytes(n) bytes (look-back state, deferred
+ *                    long-row list and a 64 MiB table of 32-bit counters used by K6 for global
+ *                    tables of 2^22..2^24 bins).  The entry points clear what they use on the first
+ *                    slice of a chunk; bnpk_tile_workspace_reset zeroes all of it.
  * A single pass over the chunk (decoupled look-back over per-tile newline counts).
  * ------------------------------------------------------------------------------------- */
 size_t bnpk_tile_workspace_bytes(size_t n);
