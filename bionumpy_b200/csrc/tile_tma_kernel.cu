@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
         }
         ex = inc - cnt;
         if (lane == 31) g_ctl[kCtlWsum + 8 * slot + gw] = inc;
-        if (gw == kGW - 1) {                                        // first newline of the halo: end of the crossing row
+        if (gw == 0) {                                              // first newline of the halo: end of the crossing row
             const int valid = min(max(staged - kTileBytes - 16 * lane, 0), 16);
             const uint32_t mm = newline_mask16(lds128(sp + kTileBytes + 16 * lane)) & ((1u << valid) - 1u);
             const unsigned b = __ballot_sync(0xffffffffu, mm != 0);
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
             int s_hi = n_rows_tile;
             if (round != n_rounds - 1) s_hi = min(s_hi, (int)((win_lo + kNlStep - (int)jr0 + (int)pm) >> ls));
             for (int s0 = s_lo; s0 < s_hi; s0 += kGT / 4) {
-                const int s = s0 + (gt >> 2);
+                const int s = s0 + 8 * ((gw + kGW - 1) & (kGW - 1)) + (lane >> 2);   // warp 0 (look-back, copies) takes rows last
                 bool act = s < s_hi;
                 int b0 = 0, e = 0;
                 if (act) {
