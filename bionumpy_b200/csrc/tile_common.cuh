@@ -144,20 +144,17 @@ __device__ __forceinline__ uint64_t lookback_finish(const LookbackArrays &l, int
     int64_t b = tile >> 5;
     uint64_t excl = 0;
     bool have = false;
-    // ---- my own block: tiles 32b .. tile-1 (lane 0 = tile-1)
-    while (true) {
+    // ---- my own block: tiles 32b .. tile-1 (lane 0 = tile-1).  Wait (a short loop: the waiting warp shares its
+    // issue slots with the warps it waits for) until every earlier tile of the block has published something.
+    {
         const bool valid = lane < i;
+        while (__any_sync(0xffffffffu, valid && (lbA >> 62) == 0))
+            if (valid && (lbA >> 62) == 0) lbA = ld_relaxed(l.tile_state + tile - 1 - lane);
         const unsigned pref = __ballot_sync(0xffffffffu, valid && (lbA >> 62) == 2);
-        const unsigned zero = __ballot_sync(0xffffffffu, valid && (lbA >> 62) == 0);
         const unsigned upto = pref ? ((pref & (0u - pref)) << 1) - 1u : 0xffffffffu;     // lanes 0..first prefix
-        if (zero & upto) {                                   // a needed predecessor has not published yet
-            if (valid) lbA = ld_relaxed(l.tile_state + tile - 1 - lane);
-            continue;
-        }
         const uint64_t v = (valid && ((1u << lane) & upto)) ? (lbA & kValueMask) : 0;
         excl = warp_sum_u64(v);
         have = pref != 0;
-        break;
     }
     // ---- whole blocks before mine (lane 0 = block b-1)
     int64_t bb = b;
