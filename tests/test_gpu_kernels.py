@@ -99,7 +99,8 @@ def test_chunk_count_big_fq(ops, big_fq_bytes, k, bins, window):
     assert np.array_equal(hist.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("k,bins,window", [(5, 1024, 0), (31, 1 << 14, 0), (31, 1 << 24, 0), (31, 1 << 14, 41)])
+@pytest.mark.parametrize("k,bins,window", [(5, 1024, 0), (31, 1 << 14, 0), (31, 1 << 15, 0), (31, 1 << 23, 0), (31, 1 << 24, 0),
+                                           (31, 1 << 14, 41)])
 @pytest.mark.parametrize("hist_mode", [0, 2])
 def test_chunk_count_synthetic(ops, k, bins, window, hist_mode):
     n = 30000

@@ -3,7 +3,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 template <int MODE>
-__global__ void k(uint32_t *out, int iters, int n_bins_log2) {
+__global__ void k(uint32_t *out, int iters, int n_bins_log2, uint32_t one) {
     extern __shared__ uint32_t hist[];
     const uint32_t nb = 1u << n_bins_log2;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
@@ -18,7 +18,8 @@ __global__ void k(uint32_t *out, int iters, int n_bins_log2) {
             uint32_t off = (x >> 10) & mm;
             if (MODE == 1) off = (off & ~0x7Cu) | (lane << 2);   // every lane its own bank
             if (MODE == 2) off = (off & ~0x7Cu) | ((lane & 15) << 2);   // 2-way
-            atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), 1u);
+            if (MODE == 3) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(hist) + off), "r"(one) : "memory");
+            else atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(hist) + off), 1u);
         }
     }
     __syncthreads();
@@ -34,9 +35,9 @@ void run(const char *name, int threads, int blocks_per_sm, int nbl) {
     cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 2000;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<MODE><<<sms * blocks_per_sm, threads, smem>>>(out, 10, nbl);
+    k<MODE><<<sms * blocks_per_sm, threads, smem>>>(out, 10, nbl, 1u);
     cudaEventRecord(e0);
-    k<MODE><<<sms * blocks_per_sm, threads, smem>>>(out, iters, nbl);
+    k<MODE><<<sms * blocks_per_sm, threads, smem>>>(out, iters, nbl, 1u);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     double n = (double)sms * blocks_per_sm * threads * iters * 8;
@@ -49,5 +50,6 @@ int main() {
     run<1>("bank-distinct", 768, 1, 14); run<1>("bank-distinct", 288, 3, 14);
     run<2>("2-way", 768, 1, 14);
     run<0>("random 2^10", 768, 1, 10);
+    run<3>("random, ATOMS.ADD reg", 768, 1, 14);
     return 0;
 }
