@@ -401,8 +401,9 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
             const int s_lo = (win_lo > (int)jr0) ? (int)((win_lo - jr0 + pm) >> ls) : 0;
             int s_hi = n_rows_tile;
             if (round != n_rounds - 1) s_hi = min(s_hi, (int)((win_lo + kNlStep - (int)jr0 + (int)pm) >> ls));
-            for (int s0 = s_lo; s0 < s_hi; s0 += kGT / 4) {
-                const int s = s0 + 8 * ((gw + kGW - 1) & (kGW - 1)) + (lane >> 2);   // warp 0 (look-back, copies) takes rows last
+            // chunks of 8 rows go round the warps 1..7; warp 0 (look-back, copies, tickets) takes none
+            for (int s0 = s_lo + 8 * (gw - 1); gw != 0 && s0 < s_hi; s0 += 8 * (kGW - 1)) {
+                const int s = s0 + (lane >> 2);
                 bool act = s < s_hi;
                 int b0 = 0, e = 0;
                 if (act) {
