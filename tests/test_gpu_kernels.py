@@ -161,6 +161,32 @@ def test_chunk_count_unaligned_chunk_pointer(ops):
         assert np.array_equal(hist.cpu().numpy(), want), shift
 
 
+def test_chunk_count_two_line_fasta(ops):
+    """lines_per_entry = 2 ('>' headers, no '+' line): long and short rows, with and without a window, both kernels
+    (the register-staged one through an unaligned view)."""
+    rng = np.random.default_rng(31)
+    parts = []
+    for r in range(1500):
+        L = int(rng.integers(0, 700)) if r % 50 else int(rng.integers(3000, 9000))
+        parts.append(f">contig{r}\n{''.join(rng.choice(list('ACGTacgt'), size=L)) if L else ''}\n")
+    chunk = np.frombuffer("".join(parts).encode("ascii"), dtype=np.uint8).copy()
+    size, starts, lens = o.two_line_fasta_split(chunk)
+    codes = o.encode_flat(o.gather_rows(chunk, starts[:, 1], lens[:, 1]), o.alphabet_lut())
+    buf = torch.empty(chunk.size + 16, dtype=torch.uint8, device="cuda")
+    for k, bins, window in ((21, 1 << 14, 0), (4, 256, 0), (11, 1 << 20, 0), (15, 1 << 12, 25)):
+        vals, _ = o.get_minimizers_fast(codes, lens[:, 1], k, window) if window else o.get_kmers(codes, lens[:, 1], k)
+        want = o.count_bucketed_flat(vals, bins) if bins != 4 ** k else o.count_encoded_flat(vals, bins)
+        for shift in (0, 3):
+            view = buf[shift: shift + chunk.size]
+            view.copy_(dev(chunk))
+            hist, status = ops.chunk_kmer_count(view, k, bins, window_size=window, lines_per_entry=2, header_char=ord(">"),
+                                                check_plus=False)
+            st = ops.read_status(status)
+            assert (st.n_records, st.n_complete_bytes, st.n_bases) == (1500, size, int(lens[:, 1].sum())), (k, shift)
+            assert st.bad_header_entry is None and st.bad_base() is None
+            assert np.array_equal(hist.cpu().numpy(), want), (k, bins, window, shift)
+
+
 def test_chunk_count_incomplete_tail_lines(ops):
     """Every possible cut of the last record: the sequence line of an incomplete entry must not count."""
     rng = np.random.default_rng(5)
