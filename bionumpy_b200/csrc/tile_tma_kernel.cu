@@ -98,7 +98,9 @@ __device__ __forceinline__ void hist_add_val(uint32_t addr, uint32_t val) { asm 
 
 // bit 7 of every byte that equals '\n' (bit 7 of the pattern is clear, so the last term can use w itself)
 __device__ __forceinline__ uint32_t newline_msb(uint32_t w) {
-    const uint32_t s = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    uint32_t x;                                                     // (w ^ 0x0A..) & 0x7F.. as ONE LOP3 (ptxas keeps one
+    asm("lop3.b32 %0, %1, 0x0A0A0A0A, 0x7F7F7F7F, 0x28;" : "=r"(x) : "r"(w));   // constant in a uniform register)
+    const uint32_t s = x + 0x7F7F7F7Fu;
     return ~(s | w) & 0x80808080u;
 }
 // exact '\n' flags of a 16-byte unit, bit i = byte i.  Per word: the zero-byte test, one IMAD that lines the four
@@ -174,15 +176,10 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
     }
     __syncthreads();
 
-    HistTarget ht;
-    ht.global = a.hist;
-    ht.smem = s_hist;
-    ht.n_bins = a.n_bins;
-    ht.mask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
-    ht.delta = 1ull;
+    const uint64_t hmask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
     const uint64_t kmask = (1ull << (2 * a.k)) - 1;
-    const bool fast = ht.mask && ht.mask <= 0x3FFFFFFFull;
-    const uint32_t m32x4 = (uint32_t)(ht.mask & kmask) << 2;       // byte-offset mask into the table
+    const bool fast = hmask && hmask <= 0x3FFFFFFFull;
+    const uint32_t m32x4 = (uint32_t)(hmask & kmask) << 2;       // byte-offset mask into the table
     const uint32_t hist_sa = smem_addr(s_hist);
     uint32_t acc_bases = 0, acc_values = 0;                         // per thread: well inside 32 bits for any chunk
     const uint32_t ls = (uint32_t)a.lpe_shift, pm = (1u << ls) - 1u;
@@ -510,8 +507,10 @@ __global__ void __launch_bounds__(kCta, 1) tile_tma_kernel(const TileArgs a) {
                                 if (t < left) {
                                     const uint32_t lo32 = __funnelshift_r(a0, a1, 2 * t), hi32 = __funnelshift_r(a1, a2, 2 * t);
                                     const uint64_t h = (((uint64_t)hi32 << 32) | lo32) & kmask;
-                                    if constexpr (HIST == 2) atomicAdd(a.hist32 + (ht.mask ? (h & ht.mask) : (h % ht.n_bins)), 1u);
-                                    else hist_add<SMEM_HIST>(ht, h);
+                                    const uint64_t b = hmask ? (h & hmask) : (h % a.n_bins);
+                                    if constexpr (HIST == 2) atomicAdd(a.hist32 + b, 1u);
+                                    else if constexpr (HIST == 1) atomicAdd(s_hist + (uint32_t)b, 1u);
+                                    else atomicAdd(a.hist + b, 1ull);
                                 }
                             }
                         }
