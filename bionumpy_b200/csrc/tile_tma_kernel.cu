@@ -135,12 +135,13 @@ __device__ __forceinline__ uint32_t encode_unit(const uint4 q, uint32_t seq16, c
         if (seq16 == 0xFFFFu) {
             bad = dif[0] | dif[1] | dif[2] | dif[3];
         } else {
-            bad = 0;
+            uint32_t acc = 0;                                       // bit i = byte i of the unit differs (as in newline_mask16)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 3; j >= 0; --j) {
                 const uint32_t nz = (((dif[j] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dif[j]) & 0x80808080u;  // byte != 0
-                bad |= msb_to_nibble(nz) & (seq16 >> (4 * j)) & 0xFu;
+                acc = __funnelshift_l(nz * 0x00204081u, acc, 4);
             }
+            bad = acc & seq16;
         }
         return codes;
     } else {
