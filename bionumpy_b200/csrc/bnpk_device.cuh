@@ -30,6 +30,7 @@ constexpr uint64_t kValueMask = (1ull << 62) - 1;
 // workspace header (uint64 words)
 constexpr int kWsTicket = 0;        // per-launch tile ticket
 constexpr int kWsDeferred = 1;      // number of deferred (long) rows
+constexpr int kWsCarry = 2;         // newlines in all tiles of the earlier launches (slices) of this chunk
 constexpr int kWsHeaderWords = 16;
 
 __device__ __forceinline__ uint64_t ld_relaxed(const uint64_t *p) {

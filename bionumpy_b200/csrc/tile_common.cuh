@@ -186,5 +186,7 @@ __device__ __forceinline__ uint64_t lookback_finish(const LookbackArrays &l, int
 bool tma_count_eligible(const TileArgs &a, bool smem_hist);
 constexpr int64_t kScratch32MaxBins = 1ll << 24;   // 64 MiB of u32 counters at the end of the workspace
 int launch_tma_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st);
+// the warp-specialised fused count (tile_ws_kernel.cu): same eligibility, the default
+int launch_ws_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st);
 
 }  // namespace bnpk

@@ -501,17 +501,22 @@ static int launch_count_enc(const TileArgs &a, bool smem_hist, cudaStream_t st) 
     return mz ? launch_tile<1, ENC, false, true>(a, st) : launch_tile<1, ENC, false, false>(a, st);
 }
 
-// BNPK_TILE_KERNEL=reg forces the register-staged kernel everywhere (A/B runs, tests of both paths)
-static bool tma_kernel_allowed() {
-    static const bool allowed = [] {
+// BNPK_TILE_KERNEL selects the fused-count kernel (A/B runs, tests of every path): "reg" = register-staged
+// everywhere, "tma" = the round-1 shared-memory-staged kernel, anything else = the warp-specialised one
+static int tile_kernel_choice() {
+    static const int choice = [] {
         const char *e = std::getenv("BNPK_TILE_KERNEL");
-        return !(e && e[0] == 'r');
+        if (e && e[0] == 'r') return 0;
+        if (e && e[0] == 't') return 1;
+        return 2;
     }();
-    return allowed;
+    return choice;
 }
+static bool tma_kernel_allowed() { return tile_kernel_choice() != 0; }
 
 static int launch_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st) {
-    if (tma_kernel_allowed() && tma_count_eligible(a, smem_hist)) return launch_tma_count(a, enc_mode, smem_hist, st);
+    if (tma_kernel_allowed() && tma_count_eligible(a, smem_hist))
+        return tile_kernel_choice() == 1 ? launch_tma_count(a, enc_mode, smem_hist, st) : launch_ws_count(a, enc_mode, smem_hist, st);
     switch (enc_mode) {
         case BNPK_ENC_ASCII_ACGT: return launch_count_enc<BNPK_ENC_ASCII_ACGT>(a, smem_hist, st);
         case BNPK_ENC_ASCII_ACTG: return launch_count_enc<BNPK_ENC_ASCII_ACTG>(a, smem_hist, st);

@@ -34,6 +34,21 @@ __global__ void __launch_bounds__(1024) k(uint32_t *out, int iters, uint32_t c1,
             } else if (MODE == 7) { // IADD3
                 a = a + b + c; b = b + c + d; c = c + d + a; d = d + a + b;
                 e = e + f + g; f = f + g + h; g = g + h + e; h = h + e + f;
+            } else if (MODE == 9) { // IDP.4A
+                a = __dp4a(a, c1, b); b = __dp4a(b, c2, c); c = __dp4a(c, c1, d); d = __dp4a(d, c2, a);
+                e = __dp4a(e, c1, f); f = __dp4a(f, c2, g); g = __dp4a(g, c1, h); h = __dp4a(h, c2, e);
+            } else if (MODE == 10) { // half LOP3, half IDP.4A
+                a = (a & b) ^ c; b = __dp4a(b, c2, c); c = (c & d) ^ a; d = __dp4a(d, c2, a);
+                e = (e & f) ^ g; f = __dp4a(f, c2, g); g = (g & h) ^ e; h = __dp4a(h, c2, e);
+            } else if (MODE == 11) { // POPC (+IADD)
+                a = __popc(a) + b; b = __popc(b) + c; c = __popc(c) + d; d = __popc(d) + a;
+                e = __popc(e) + f; f = __popc(f) + g; g = __popc(g) + h; h = __popc(h) + e;
+            } else if (MODE == 12) { // 2 LOP3 : 1 IMAD : 1 IDP.4A (the newline test mix)
+                a = (a & b) ^ c; b = (b | c) ^ d; c = c * c1 + d; d = __dp4a(d, c2, a);
+                e = (e & f) ^ g; f = (f | g) ^ h; g = g * c1 + h; h = __dp4a(h, c2, e);
+            } else if (MODE == 13) { // FLO/ffs (+IADD)
+                a = __ffs(a) + b; b = __ffs(b) + c; c = __ffs(c) + d; d = __ffs(d) + a;
+                e = __ffs(e) + f; f = __ffs(f) + g; g = __ffs(g) + h; h = __ffs(h) + e;
             } else if (MODE == 8) { // SHF.R.U32 plain shift
                 a = (a >> 3) ^ 0; b = b >> 5; c = c >> 7; d = d >> 9; e = e >> 3; f = f >> 5; g = g >> 7; h = h >> 9;
                 a += c1; b += c1; c += c1; d += c1; e += c2; f += c2; g += c2; h += c2;
@@ -62,5 +77,6 @@ void run(const char *name, int ops_per_unroll) {
 int main() {
     run<0>("SHF funnel", 8); run<1>("LOP3", 8); run<2>("IMAD lo", 8); run<3>("IMAD.HI (+IADD)", 8); run<4>("LOP3 + IMAD", 8);
     run<5>("LOP3 + IMAD.HI (+IADD)", 8); run<6>("PRMT", 8); run<7>("IADD3", 8); run<8>("SHF.R shift (+IADD)", 8);
+    run<9>("IDP.4A", 8); run<10>("LOP3 + IDP.4A", 8); run<11>("POPC (+IADD)", 8); run<12>("2 LOP3 + IMAD + IDP.4A", 8); run<13>("ffs (+IADD)", 8);
     return 0;
 }
