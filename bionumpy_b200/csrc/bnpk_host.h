@@ -12,6 +12,13 @@ extern std::atomic<uint64_t> g_launches;
 int set_err(int code, const char *msg);
 int cuda_fail(cudaError_t e, const char *what);
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device)
+int ensure_dyn_smem(const void *kernel, int bytes);
+#define BNPK_DYN_SMEM(kern, bytes)                                            \
+    do {                                                                      \
+        int rc__ = ::bnpk::ensure_dyn_smem((const void *)(kern), (int)(bytes)); \
+        if (rc__) return rc__;                                                \
+    } while (0)
 
 #define BNPK_CUDA(expr)                                             \
     do {                                                            \

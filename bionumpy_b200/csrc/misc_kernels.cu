@@ -43,6 +43,19 @@ void profile_after(cudaStream_t st) {
     cudaEventRecord(g_prof_events.back().second, st);
 }
 
+int ensure_dyn_smem(const void *kernel, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, int>> done;                // (kernel, device) pairs already raised
+    int dev = 0;
+    BNPK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> l(mu);
+    for (const auto &e : done)
+        if (e.first == kernel && e.second == dev) return 0;
+    BNPK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.emplace_back(kernel, dev);
+    return 0;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -338,11 +351,7 @@ int bnpk_bincount(const int64_t *values, size_t n, int64_t n_bins, int hist_mode
     const bool sm = use_smem_hist(n_bins, hist_mode);
     const size_t want = (n + 511) / 512;
     if (sm) {
-        static thread_local bool attr_done = false;
-        if (!attr_done) {
-            BNPK_CUDA(cudaFuncSetAttribute(bincount_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
-        }
+        BNPK_DYN_SMEM(bincount_kernel<true>, 200 * 1024);
         const size_t smem = (size_t)n_bins * 4;
         int per_sm = 1;
         BNPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bincount_kernel<true>, 512, smem));

@@ -289,11 +289,7 @@ static int launch_rows_t(const RowArgs &a, size_t est_rows, cudaStream_t st) {
     auto kern = rows_kernel<RM, ENC, SMEM_HIST, DEFERRED>;
     constexpr bool COUNTING = (RM == RM_COUNT || RM == RM_COUNT_MIN);
     const size_t smem = rows_smem_bytes(COUNTING, SMEM_HIST, a.n_bins);
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
-        BNPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    BNPK_DYN_SMEM(kern, 200 * 1024);
     int per_sm = 1;
     BNPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRowThreads, smem));
     if (per_sm < 1) return set_err(BNPK_E_BINS, "rows kernel does not fit shared memory");

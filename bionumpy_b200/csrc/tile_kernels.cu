@@ -476,11 +476,7 @@ template <int MODE, int ENC, bool SMEM_HIST, bool MINIMIZER>
 static int launch_tile(const TileArgs &a, cudaStream_t st) {
     auto kern = tile_kernel<MODE, ENC, SMEM_HIST, MINIMIZER>;
     const size_t smem = tile_smem_bytes(MODE, a.n_bins, SMEM_HIST);
-    static thread_local bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        BNPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    BNPK_DYN_SMEM(kern, 200 * 1024);
     int per_sm = 1;
     BNPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCtaThreads, smem));
     if (per_sm < 1) return set_err(BNPK_E_BINS, "tile kernel does not fit shared memory");

@@ -554,11 +554,7 @@ template <int ENC, int HIST>
 static int launch_t(const TileArgs &a, cudaStream_t st) {
     auto kern = tile_tma_kernel<ENC, HIST>;
     const size_t smem = (size_t)kFixedBytes + (HIST == 1 ? ((a.n_bins * 4 + 127) & ~(uint64_t)127) : 0);
-    static thread_local bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        BNPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFixedBytes + kMaxBins * 4));
-        attr_done = true;
-    }
+    BNPK_DYN_SMEM(kern, kFixedBytes + kMaxBins * 4);
     const int64_t n_tiles = a.tile_end - a.tile_begin;
     if (n_tiles <= 0) return 0;
     const int64_t grid = std::min<int64_t>((n_tiles + kGroups - 1) / kGroups, (int64_t)sm_count());

@@ -2,19 +2,22 @@
 //
 // One persistent CTA per SM.  The chunk streams through a ring of kNS shared-memory slots (16 KiB tile + 512 B of
 // halo so the one row that crosses the tile end can finish in the slot) filled by cp.async.bulk (TMA).  Four kinds
-// of warps work on different tiles of the ring at the same time and hand slots on through mbarriers only -- there is
-// no CTA- or group-wide barrier on the path of a tile, and no warp executes another role's code:
+// of warps work on different tiles of the ring at the same time; slots are handed on through mbarriers and small
+// shared-memory queues only -- there is no CTA-wide barrier on the path of a tile, and no warp runs another role's code:
 //
-//   P  (1 lane)   takes tile tickets in order, waits for a slot to be free, starts its bulk copy            -> full[slot]
-//   S  (4 warps)  exact newline masks of the tile (128 B per lane), prefix over the four warps (the only named
-//                 barrier: the four scan warps), sorted newline list of the tile, the tile's newline count to the
-//                 workspace (one relaxed store), first newline of the halo                                  -> scanned[slot]
-//   F  (1 warp)   line index of the tile's first byte: this CTA's previous tile + the counts every CTA published
+//   P  (1 lane)   tiles are dealt round-robin over the CTAs; waits for a slot to be free, starts its bulk copy -> full[slot]
+//   S  (2 groups of 4 warps, alternate tiles) exact newline masks (128 B per lane), prefix over the group's four
+//                 warps (the only named barrier: those four warps), sorted newline list of the tile, the tile's
+//                 newline count to the workspace (one relaxed store), first newline of the halo            -> scanned[slot]
+//   F  (1 warp)   line index of the tile's first byte = this CTA's previous tile + the counts every CTA published
 //                 for the tiles in between (loads issued one tile ahead); entry structure of the newlines before
-//                 the first row, last complete entry, first byte of the chunk                               -> ready[slot]
-//   R  (16 warps, 4 teams of 4; team t takes every 4th tile of the ring) per chunk of 8 rows: one lane per newline
-//                 validates '@' / '+', four lanes per row read the row's 16-byte units from the slot, encode + validate
-//                 them, pass the 2-bit code words round with shuffles; every k-mer is SHF + LOP3 + ATOMS   -> free[slot]
+//                 the first row, last complete entry, first byte of the chunk; cuts the tile's rows into chunks
+//                 of 32 and deals them round the row warps' queues                                          -> queue[warp]
+//   R  (kRW warps) pops a chunk: ONE LANE PER ROW.  The lane validates its entry ('@', '+'), then walks its row's
+//                 16-byte units in the slot: encode + validate (first and last unit masked, the others whole), a
+//                 three-word window of 2-bit codes in registers, and every k-mer of a 16-base block is
+//                 SHF + LOP3 + ATOMS.  No shuffles, no per-row cooperation.  The last chunk of a tile frees its slot
+//                                                                                                           -> free[slot]
 //
 // The warps with the most urgent work have the highest warp ids (the SM arbiter favours them): P, F, S, then R.
 // Replaces io/one_line_buffer.py:44-71,139-182 + encodings/alphabet_encoding.py:34-46 + sequence/kmers.py:105-126 +
@@ -28,34 +31,42 @@ constexpr int kNS = 8;                          // ring slots
 constexpr int kHalo = 512;
 constexpr int kSlot = kTileBytes + kHalo;
 constexpr int kNlCap = 1024;                    // newline positions of one tile kept in shared memory
-constexpr int kWinStep = 960;                   // tiles with more newlines are walked in windows of the list
+constexpr int kWinRows = 224;                   // tiles with more newlines are walked in windows of this many rows
 constexpr int kRowMax = 1024;                   // longer rows go to the deferred (one warp per segment) pass
 constexpr int kMaxBins = 16384;
 constexpr uint32_t kNoCross = 0xFFFFFFFFu;
-constexpr int kSW = 4;                          // scan warps: 4 KiB of the tile each, 128 B per lane
-constexpr int kTeams = 4, kTeamWarps = 4;       // row warps
-constexpr int kRW = kTeams * kTeamWarps;
-constexpr int kFWarp = kRW + kSW, kPWarp = kFWarp + 1;
+constexpr int kSW = 4;                          // warps of a scan group: 4 KiB of the tile each, 128 B per lane
+constexpr int kSG = 2;                          // scan groups
+constexpr int kRW = 8;                          // row warps
+constexpr int kQD = 8;                          // queue depth per row warp
+constexpr int kFWarp = kRW + kSG * kSW, kPWarp = kFWarp + 1;
 constexpr int kWarps = kPWarp + 1;
 constexpr int kCta = kWarps * 32;
 constexpr int kFK = 6;                          // look-back loads per lane kept in flight (192 tiles)
 static_assert(kSW * 4096 == kTileBytes, "scan geometry");
-static_assert((kNS & (kNS - 1)) == 0, "ring size");
+static_assert((kNS & (kNS - 1)) == 0 && (kQD & (kQD - 1)) == 0 && kRW <= 32, "ring sizes");
+static_assert(kWinRows % 32 == 0 && 4 * kWinRows + 64 <= kNlCap, "list window");
 
 // per-slot descriptor (32-bit words)
-constexpr int kDTile = 0;                       // P: tile index, -1 = end of the launch
+constexpr int kDTile = 0;                       // P: tile index, 0xFFFFFFFF = end of the launch
 constexpr int kDCount = 1;                      // S: newlines in the tile proper
 constexpr int kDCross = 2;                      // S: first newline of the halo (slot-relative) or kNoCross
+constexpr int kDRemain = 3;                     // F: chunks of the tile not finished yet
 constexpr int kDBase = 4;                       // F: int64 line index of the tile's first byte
 constexpr int kDescWords = 8;
+// queue records: tag (push number + 1) << 16 | slot << 12 | chunk
+constexpr uint32_t kChunkWhole = 0xFFFu;        // the whole tile, walked in windows (more newlines than the list holds)
+constexpr uint32_t kChunkEnd = 0xFFEu;
 // shared memory after the histogram (bytes)
 constexpr int kOffSlots = 0;
 constexpr int kOffList = kOffSlots + kNS * kSlot;
 constexpr int kOffDesc = kOffList + kNS * kNlCap * 2;
-constexpr int kOffBar = kOffDesc + kNS * kDescWords * 4;      // full | scanned | ready | free, kNS each
-constexpr int kOffWsum = kOffBar + 4 * kNS * 8;
-constexpr int kOffLut = kOffWsum + 2 * kSW * 4;
+constexpr int kOffBar = kOffDesc + kNS * kDescWords * 4;      // full | scanned | free, kNS each
+constexpr int kOffWsum = kOffBar + 3 * kNS * 8;               // [group][2][kSW]
+constexpr int kOffQueue = kOffWsum + kSG * 2 * kSW * 4;       // [kRW][kQD] records, then [kRW] consumed counters
+constexpr int kOffLut = kOffQueue + kRW * kQD * 4 + kRW * 4;
 constexpr int kFixedBytes = kOffLut + 256;
+static_assert(kOffBar % 8 == 0 && kOffLut % 16 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -67,24 +78,37 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
+// the hint lets the hardware park the thread instead of spinning through issue slots the other warps need
+#define BNPK_MBAR_WAIT_BODY                                                      \
+    asm volatile(                                                                \
+        "{\n"                                                                    \
+        ".reg .pred p;\n"                                                        \
+        "WAIT_%=:\n"                                                             \
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"            \
+        "@p bra DONE_%=;\n"                                                      \
+        "bra WAIT_%=;\n"                                                         \
+        "DONE_%=:\n"                                                             \
+        "}\n" ::"r"(bar), "r"(parity), "r"(20000u)                               \
+        : "memory")
+// one copy per waiting role, so that profiles tell the waits apart
+__device__ __forceinline__ void mbar_wait_free(uint32_t bar, uint32_t parity) {
+    BNPK_MBAR_WAIT_BODY;
+}
+__device__ __forceinline__ void mbar_wait_full_f(uint32_t bar, uint32_t parity) {
+    BNPK_MBAR_WAIT_BODY;
+}
+__device__ __forceinline__ void mbar_wait_scanned(uint32_t bar, uint32_t parity) {
+    BNPK_MBAR_WAIT_BODY;
+}
+__device__ __forceinline__ void mbar_wait_full_s(uint32_t bar, uint32_t parity) {
+    BNPK_MBAR_WAIT_BODY;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void scan_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSW * 32) : "memory"); }
+__device__ __forceinline__ void scan_bar(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kSW * 32) : "memory"); }
 __device__ __forceinline__ uint4 lds128(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 // PRMT without the selector clean-up __byte_perm adds (all selectors used here are in range)
 __device__ __forceinline__ uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
@@ -98,8 +122,8 @@ __device__ __forceinline__ void hist_inc(uint32_t addr) { asm volatile("red.shar
 __device__ __forceinline__ void hist_add_val(uint32_t addr, uint32_t val) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory"); }
 
 // Integer pipes of an SM sub-partition (tools/micro/pipe_bench.cu, B200): LOP3/SHF/PRMT/IADD3 (ALU pipe) and IMAD /
-// IDP (FMA pipe) each issue one warp instruction every two cycles.  This path is all integer work: instruction
-// count, and how it splits over the two pipes, sets the kernel time -- not bytes.
+// IDP.4A (FMA pipe) each issue one warp instruction every two cycles, any mix of the two 0.65 per cycle; POPC one
+// every 8 cycles, ffs (BREV + FLO) one every 16.  This path is all integer work: instruction count sets the time.
 
 // bit 7 of every byte that equals '\n' (bit 7 of the pattern is clear, so the last term can use w itself)
 __device__ __forceinline__ uint32_t newline_msb(uint32_t w) {
@@ -108,22 +132,14 @@ __device__ __forceinline__ uint32_t newline_msb(uint32_t w) {
     const uint32_t s = x + 0x7F7F7F7Fu;
     return ~(s | w) & 0x80808080u;
 }
-// exact '\n' flags of a 16-byte unit, bit i = byte i
+// exact '\n' flags of a 16-byte unit, bit i = byte i: the flag bytes are 0x80 or 0, one IDP.4A per word weighs
+// them into place (4 instructions per word, two of them on the FMA pipe)
 __device__ __forceinline__ uint32_t newline_mask16(const uint4 q) {
-#ifdef BNPK_WS_DP4A
-    // the flag bytes are 0x80 or 0: one IDP.4A per word weighs them into place (FMA pipe)
     uint32_t lo = __dp4a(newline_msb(q.x), 0x08040201u, 0u);
     lo = __dp4a(newline_msb(q.y), 0x80402010u, lo);                // 128 * (flags of bytes 0..7)
     uint32_t hi = __dp4a(newline_msb(q.z), 0x08040201u, 0u);
     hi = __dp4a(newline_msb(q.w), 0x80402010u, hi);                // 128 * (flags of bytes 8..15)
     return (lo >> 7) | (hi << 1);
-#else
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    uint32_t acc = 0;
-#pragma unroll
-    for (int j = 3; j >= 0; --j) acc = __funnelshift_l(newline_msb(w[j]) * 0x00204081u, acc, 4);
-    return acc & 0xFFFFu;
-#endif
 }
 
 // Conflict-free read of a lane's 64 bytes (LDS.128 j fetches unit (j + lane/2) & 3) -> exact 64-bit newline mask.
@@ -165,12 +181,13 @@ __device__ __forceinline__ void emit_positions(uint64_t m, uint32_t li, uint32_t
     }
 }
 
-// 16-byte unit -> 32 bits of 2-bit codes; `bad` != 0 iff a byte selected by seq16 is outside the alphabet (exact).
+// 16-byte unit -> 32 bits of 2-bit codes; `bad` != 0 iff a byte of the unit (WHOLE) or a byte selected by seq16
+// (!WHOLE) is outside the alphabet (exact).
 // ASCII alphabets: bits 1-2 of a letter are a Gray code of its index (A 00, C 01, G 11, T 10).  Per word: one LOP3
 // isolates them, one IMAD packs the four fields into the top byte, one IMAD lines them up as PRMT selector nibbles,
 // PRMT looks the expected lower-case letter up, LOP3 compares it with the case-folded input; per unit: three PRMT
 // gather the packed bytes and (ACGT only) two ops turn Gray into binary for all sixteen bases at once.
-template <int ENC>
+template <int ENC, bool WHOLE>
 __device__ __forceinline__ uint32_t encode_unit(const uint4 q, uint32_t seq16, const uint8_t *s_lut, uint32_t &bad) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     if constexpr (ENC == BNPK_ENC_ASCII_ACGT || ENC == BNPK_ENC_ASCII_ACTG || ENC == BNPK_ENC_CODES) {
@@ -189,20 +206,55 @@ __device__ __forceinline__ uint32_t encode_unit(const uint4 q, uint32_t seq16, c
         }
         uint32_t codes = prmt(prmt(pk[0], pk[1], 0x0073), prmt(pk[2], pk[3], 0x0073), 0x5410);
         if constexpr (ENC == BNPK_ENC_ASCII_ACGT) codes ^= (codes >> 1) & 0x55555555u;
-        if (seq16 == 0xFFFFu) {
+        if constexpr (WHOLE) {
             bad = dif[0] | dif[1] | dif[2] | dif[3];
         } else {
-            uint32_t acc = 0;                                       // bit i = byte i of the unit differs
+            // byte != 0 flags (bit 7 of every byte), weighed into a 16-bit mask like the newline flags
+            uint32_t nz[4];
 #pragma unroll
-            for (int j = 3; j >= 0; --j) {
-                const uint32_t nz = (((dif[j] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dif[j]) & 0x80808080u;  // byte != 0
-                acc = __funnelshift_l(nz * 0x00204081u, acc, 4);
-            }
-            bad = acc & seq16;
+            for (int j = 0; j < 4; ++j) nz[j] = (((dif[j] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | dif[j]) & 0x80808080u;
+            const uint32_t lo = __dp4a(nz[1], 0x80402010u, __dp4a(nz[0], 0x08040201u, 0u));
+            const uint32_t hi = __dp4a(nz[3], 0x80402010u, __dp4a(nz[2], 0x08040201u, 0u));
+            bad = ((lo >> 7) | (hi << 1)) & seq16;
         }
         return codes;
     } else {
-        return encode_unit_seq<ENC>(w, seq16, s_lut, bad);
+        return encode_unit_seq<ENC>(w, WHOLE ? 0xFFFFu : seq16, s_lut, bad);
+    }
+}
+
+// Checks of a tile that do not belong to one of its rows, by lanes 0..3 of a warp that owns the slot: entry
+// structure at the newlines before the first row's (one_line_buffer.py:155-173, fastq_buffer.py:38-45), the
+// chunk's first byte, the end of the tile's last complete entry (-> FileBuffer.size, one_line_buffer.py:67-69).
+__device__ __forceinline__ void tile_head_checks(const TileArgs &a, const uint8_t *sp, const uint16_t *list, int64_t tile,
+                                                 uint32_t count, uint64_t base, uint32_t ls, uint32_t want, int lane,
+                                                 unsigned long long &complete) {
+    const uint32_t pm = (1u << ls) - 1u;
+    const size_t byte0 = (size_t)tile * kTileBytes;
+    const uint32_t base_phase = (uint32_t)base & pm;
+    const int64_t q0 = (int64_t)(base >> ls);
+    const uint32_t jr0 = (want - base_phase) & pm;                   // first newline (rel) that precedes a field line
+    if ((uint32_t)lane < jr0 && (uint32_t)lane < count) {
+        const uint32_t p = list[lane];
+        const uint32_t phase = (base_phase + (uint32_t)lane) & pm;
+        const bool chk_h = phase == pm, chk_p = a.check_plus && phase == 1u;
+        if ((chk_h || chk_p) && byte0 + p + 1 < a.n) {
+            const uint32_t c = sp[p + 1];
+            if (chk_h && c != a.header_char)
+                atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], (long long)(q0 + ((base_phase + (uint32_t)lane + 1u) >> ls)));
+            if (chk_p && c != '+')
+                atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY], (long long)(q0 + ((base_phase + (uint32_t)lane) >> ls)));
+        }
+    }
+    if (lane == 0) {
+        if (count > 0) {                                              // last complete entry of the tile
+            const uint32_t last = count - 1u;
+            const uint32_t back = (base_phase + last - pm) & pm;
+            if (last >= back && last - back < (uint32_t)kNlCap)
+                complete = max(complete, (unsigned long long)(byte0 + list[last - back] + 1));
+        }
+        if (tile == 0 && a.n > 0 && sp[0] != a.header_char)
+            atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
     }
 }
 
@@ -212,27 +264,28 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
     constexpr bool SMEM_HIST = HIST == 1;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem_raw);
-    uint8_t *s_fixed = smem_raw + (SMEM_HIST ? ((a.n_bins * 4 + 127) & ~(uint64_t)127) : 0);
+    uint8_t *s_fixed = smem_raw + (SMEM_HIST ? ((a.n_bins * 4 + 4 + 127) & ~(uint64_t)127) : 0);   // table + a spare word
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *s_slots = s_fixed + kOffSlots;
     uint16_t *s_list = reinterpret_cast<uint16_t *>(s_fixed + kOffList);
     volatile uint32_t *s_desc = reinterpret_cast<volatile uint32_t *>(s_fixed + kOffDesc);
-    const uint32_t bar_full = smem_addr(s_fixed + kOffBar), bar_scanned = bar_full + 8 * kNS,
-                   bar_ready = bar_full + 16 * kNS, bar_free = bar_full + 24 * kNS;
+    const uint32_t bar_full = smem_addr(s_fixed + kOffBar), bar_scanned = bar_full + 8 * kNS, bar_free = bar_full + 16 * kNS;
     volatile uint32_t *s_wsum = reinterpret_cast<volatile uint32_t *>(s_fixed + kOffWsum);
+    volatile uint32_t *s_queue = reinterpret_cast<volatile uint32_t *>(s_fixed + kOffQueue);
+    volatile uint32_t *s_qcons = s_queue + kRW * kQD;
     uint8_t *s_lut = s_fixed + kOffLut;
     uint64_t *tile_state = a.ws + kWsHeaderWords;
 
     if (ENC == BNPK_ENC_LUT && tid < 256) s_lut[tid] = a.lut[tid];
     if (SMEM_HIST)
         for (uint32_t b = tid; b < a.n_bins; b += kCta) s_hist[b] = 0;
+    if (tid < kRW * kQD + kRW) s_queue[tid] = 0;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_scanned + 8 * s, kSW);
-            mbar_init(bar_ready + 8 * s, 1);
-            mbar_init(bar_free + 8 * s, kTeamWarps);
+            mbar_init(bar_free + 8 * s, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -244,18 +297,16 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
 
     if (warp == kPWarp) {
         // ============================ P: tickets and bulk copies ============================================
+        // Tiles are dealt round-robin over the CTAs (CTA c takes tiles c, c + G, c + 2G, ...): no ticket counter --
+        // one global atomic per tile on a single address cost ~1.4 us of latency each and bounded the whole kernel.
+        // Every CTA is resident (grid <= SM count), so the look-back never waits for a tile nobody has started.
         if (lane == 0) {
-            auto take_ticket = [&]() -> int32_t {
-                const unsigned long long t = (unsigned long long)a.tile_begin + atomicAdd((unsigned long long *)(a.ws + kWsTicket), 1ull);
-                return (int32_t)min(t, (unsigned long long)0x7FFFFFFF);
-            };
             int nend = 0;
-            int32_t t = take_ticket();
             for (uint32_t seq = 0;; ++seq) {
                 const uint32_t slot = seq & (kNS - 1), use = seq / kNS;
-                if (use > 0) mbar_wait(bar_free + 8 * slot, (use - 1u) & 1u);
-                if (t < tile_end) {
-                    const int32_t t_next = take_ticket();            // in flight while this tile's copy is issued
+                if (use > 0) mbar_wait_free(bar_free + 8 * slot, (use - 1u) & 1u);
+                const int64_t t = a.tile_begin + (int64_t)blockIdx.x + (int64_t)seq * gridDim.x;
+                if (t < (int64_t)tile_end) {
                     const size_t byte0 = (size_t)t * kTileBytes;
                     const uint32_t bytes = (uint32_t)min((size_t)kSlot, a.n - byte0) & ~15u;
                     s_desc[slot * kDescWords + kDTile] = (uint32_t)t;
@@ -265,125 +316,114 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                     } else {
                         mbar_arrive(bar_full + 8 * slot);
                     }
-                    t = t_next;
-                } else {                                              // one end marker per row team
+                } else {                                              // one end marker per scan group
                     s_desc[slot * kDescWords + kDTile] = 0xFFFFFFFFu;
                     mbar_arrive(bar_full + 8 * slot);
-                    if (++nend == kTeams) break;
+                    if (++nend == kSG) break;
                 }
             }
         }
     } else if (warp == kFWarp) {
-        // ============================ F: line index of every tile of this CTA ===============================
-        int64_t prevA = a.tile_begin - 1;                            // this CTA's previous tile
-        uint64_t incl = a.tile_begin > 0 ? a.ws[kWsCarry] : 0ull;    // lines in all tiles up to and including tileB's predecessor chain
-        uint64_t vB[kFK];
-        int64_t tileB = -1, prevB = -1;
-        uint32_t slotB = 0, parB = 0;
-        bool haveB = false;
+        // ============================ F: line index of every tile of this CTA; deals the rows out ===========
+        // A single warp per CTA, once per tile: its latency per tile bounds the whole ring, so the path from "the scan
+        // warps are done" to "the row warps have their chunks" is kept to one shared-memory read and a few stores; the
+        // sum over the other CTAs' counts is complete before that (loads issued one tile ahead, 32-bit REDUX).
+        const int64_t G = (int64_t)gridDim.x;
+        uint64_t incl = a.tile_begin > 0 ? a.ws[kWsCarry] : 0ull;    // lines in every tile before `prev + 1`
+        int64_t prev = a.tile_begin - 1, tile = a.tile_begin + (int64_t)blockIdx.x;
         unsigned long long f_complete = 0;
-        int ends = 0;
-        for (uint32_t seq = 0;; ++seq) {
-            const uint32_t slot = seq & (kNS - 1), par = (seq / kNS) & 1u;
-            // ---- A(seq): which tile, and the loads of every count published between it and its predecessor
-            mbar_wait(bar_full + 8 * slot, par);
-            const int32_t tileA = (int32_t)s_desc[slot * kDescWords + kDTile];
-            uint64_t vA[kFK];
+        uint32_t next_rw = 0;                                        // row warp that gets the next chunk
+        uint32_t pushes = 0;                                         // lane w: records pushed to row warp w
+        auto push = [&](uint32_t rec) {                              // by the lane whose number is the row warp
+            while (pushes - s_qcons[lane] >= (uint32_t)kQD) __nanosleep(64);
+            s_queue[lane * kQD + (pushes & (kQD - 1))] = ((pushes + 1u) << 16) | rec;
+            ++pushes;
+        };
+        auto issue = [&](uint64_t *v, int64_t lo, int64_t hi) {      // counts of the tiles lo+1 .. hi-1
 #pragma unroll
             for (int i = 0; i < kFK; ++i) {
-                const int64_t idx = prevA + 1 + lane + 32 * i;
-                vA[i] = (tileA >= 0 && idx < (int64_t)tileA) ? ld_relaxed(tile_state + idx) : kFlagAgg;
+                const int64_t idx = lo + 1 + lane + 32 * i;
+                v[i] = (hi < (int64_t)tile_end && idx < hi) ? ld_relaxed(tile_state + idx) : kFlagAgg;
             }
-            // ---- B(seq - 1): finish the previous tile (its loads had a whole tile period to land)
-            if (haveB) {
-                mbar_wait(bar_scanned + 8 * slotB, parB);
-                const uint32_t count = s_desc[slotB * kDescWords + kDCount];
-                uint64_t sum = 0;
+        };
+        uint64_t vC[kFK];
+        issue(vC, prev, tile);
+        for (uint32_t seq = 0; tile < (int64_t)tile_end; ++seq) {
+            const uint32_t slot = seq & (kNS - 1), par = (seq / kNS) & 1u;
+            uint64_t vN[kFK];
+            issue(vN, tile, tile + G);                                // the next tile's, a tile period ahead
+            uint32_t sum32 = 0;
 #pragma unroll
-                for (int i = 0; i < kFK; ++i) {
-                    uint64_t v = vB[i];
-                    const int64_t idx = prevB + 1 + lane + 32 * i;
-                    while ((v >> 62) == 0) v = ld_relaxed(tile_state + idx);
-                    sum += v & kValueMask;
-                }
-                for (int64_t idx = prevB + 1 + lane + 32 * kFK; idx < tileB; idx += 32) {   // rare: a long gap
+            for (int i = 0; i < kFK; ++i) {
+                uint64_t v = vC[i];
+                const int64_t idx = prev + 1 + lane + 32 * i;
+                while ((v >> 62) == 0) v = ld_relaxed(tile_state + idx);
+                sum32 += (uint32_t)v;                                 // a tile has at most 16384 newlines
+            }
+            uint64_t base = incl + __reduce_add_sync(0xffffffffu, sum32);
+            if (tile - prev - 1 > 32 * kFK) {                         // rare: more CTAs than the loads in flight cover
+                uint64_t sum = 0;
+                for (int64_t idx = prev + 1 + lane + 32 * kFK; idx < tile; idx += 32) {
                     uint64_t v = ld_relaxed(tile_state + idx);
                     while ((v >> 62) == 0) v = ld_relaxed(tile_state + idx);
                     sum += v & kValueMask;
                 }
-                const uint64_t base = incl + warp_sum_u64(sum);
-                incl = base + count;
-                const uint8_t *sp = s_slots + slotB * kSlot;
-                const uint16_t *list = s_list + slotB * kNlCap;
-                const size_t byte0 = (size_t)tileB * kTileBytes;
-                const uint32_t base_phase = (uint32_t)base & pm;
-                const int64_t q0 = (int64_t)(base >> ls);
-                const uint32_t jr0 = (want - base_phase) & pm;       // first newline (rel) that precedes a field line
-                // entry structure at the newlines before the first row's (one_line_buffer.py:155-173, fastq_buffer.py:38-45)
-                if ((uint32_t)lane < jr0 && (uint32_t)lane < count) {
-                    const uint32_t p = list[lane];
-                    const uint32_t phase = (base_phase + (uint32_t)lane) & pm;
-                    const bool chk_h = phase == pm, chk_p = a.check_plus && phase == 1u;
-                    if ((chk_h || chk_p) && byte0 + p + 1 < a.n) {
-                        const uint32_t c = sp[p + 1];
-                        if (chk_h && c != a.header_char)
-                            atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], (long long)(q0 + ((base_phase + (uint32_t)lane + 1u) >> ls)));
-                        if (chk_p && c != '+')
-                            atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY], (long long)(q0 + ((base_phase + (uint32_t)lane) >> ls)));
-                    }
-                }
-                if (lane == 0) {
-                    if (count > 0) {                                  // last complete entry of the tile
-                        const uint32_t last = count - 1u;
-                        const uint32_t back = (base_phase + last - pm) & pm;
-                        if (last >= back && last - back < (uint32_t)kNlCap)
-                            f_complete = max(f_complete, (unsigned long long)(byte0 + list[last - back] + 1));
-                    }
-                    if (tileB == 0 && a.n > 0 && sp[0] != a.header_char)
-                        atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], 0ll);
-                    if (tileB == a.n_tiles_total - 1) a.status[BNPK_ST_N_LINES] = (int64_t)(base + count);
-                    if (tileB == (int64_t)tile_end - 1) a.ws[kWsCarry] = base + count;
-                    *reinterpret_cast<volatile uint64_t *>(s_desc + slotB * kDescWords + kDBase) = base;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_ready + 8 * slotB);
+                base += warp_sum_u64(sum);
             }
-            if (tileA < 0) {
-                if (lane == 0) mbar_arrive(bar_ready + 8 * slot);
-                haveB = false;
-                if (++ends == kTeams) break;
-                continue;
+            mbar_wait_scanned(bar_scanned + 8 * slot, par);
+            const uint32_t count = s_desc[slot * kDescWords + kDCount];
+            incl = base + count;
+            const uint32_t jr0 = (want - (uint32_t)base) & pm;        // first newline (rel) that precedes a field line
+            const uint32_t n_rows = count > jr0 ? ((count - 1u - jr0) >> ls) + 1u : 0u;
+            const bool whole = count > (uint32_t)kNlCap;
+            const uint32_t n_chunks = whole ? 1u : (n_rows + 31u) >> 5;
+            if (lane == 0) {
+                *reinterpret_cast<volatile uint64_t *>(s_desc + slot * kDescWords + kDBase) = base;
+                s_desc[slot * kDescWords + kDRemain] = n_chunks;
+            }
+            __threadfence_block();
+            __syncwarp();
+            // chunk c goes to row warp (next_rw + c) % kRW; lane w pushes row warp w's records in order
+            if (lane < kRW) {
+                for (uint32_t c = ((uint32_t)lane + kRW - next_rw) % kRW; c < n_chunks; c += kRW)
+                    push((slot << 12) | (whole ? kChunkWhole : c));
+            }
+            next_rw = (next_rw + n_chunks) % kRW;
+            // off the critical path
+            if (n_chunks == 0) {                                      // rare: no row starts in this tile; nobody else looks at it
+                tile_head_checks(a, s_slots + slot * kSlot, s_list + slot * kNlCap, tile, count, base, ls, want, lane, f_complete);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free + 8 * slot);
+            }
+            if (lane == 0) {
+                if (tile == a.n_tiles_total - 1) a.status[BNPK_ST_N_LINES] = (int64_t)(base + count);
+                if (tile == (int64_t)tile_end - 1) a.ws[kWsCarry] = base + count;
             }
 #pragma unroll
-            for (int i = 0; i < kFK; ++i) vB[i] = vA[i];
-            tileB = tileA; prevB = prevA; slotB = slot; parB = par; haveB = true;
-            prevA = tileA;
+            for (int i = 0; i < kFK; ++i) vC[i] = vN[i];
+            prev = tile;
+            tile += G;
         }
+        if (lane < kRW) push(kChunkEnd);
         if (lane == 0 && f_complete)
             atomicMax((unsigned long long *)&a.status[BNPK_ST_N_COMPLETE_BYTES], f_complete);
     } else if (warp >= kRW) {
         // ============================ S: newline masks, sorted newline list, tile count ======================
-        const int sw = warp - kRW;
+        const int group = (warp - kRW) / kSW, sw = (warp - kRW) % kSW;
         ScanLane sl;
         sl.init(lane);
-        int ends = 0;
-        for (uint32_t seq = 0;; ++seq) {
+        for (uint32_t seq = (uint32_t)group;; seq += kSG) {
             const uint32_t slot = seq & (kNS - 1), par = (seq / kNS) & 1u;
-            mbar_wait(bar_full + 8 * slot, par);
+            mbar_wait_full_s(bar_full + 8 * slot, par);
             const int32_t tile = (int32_t)s_desc[slot * kDescWords + kDTile];
-            if (tile < 0) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_scanned + 8 * slot);
-                if (++ends == kTeams) break;
-                continue;
-            }
+            if (tile < 0) break;
             uint8_t *sp = s_slots + slot * kSlot;
             const size_t byte0 = (size_t)tile * kTileBytes;
             const int staged = (int)min((size_t)kSlot, a.n - byte0);
             if (staged & 15) {                                        // the chunk's last bytes: not a multiple of 16
                 const int t0 = staged & ~15;
                 if (sw == 0 && lane < (staged & 15)) sp[t0 + lane] = a.chunk[byte0 + t0 + lane];
-                scan_bar();
+                scan_bar(group);
             }
             const uint8_t *pb = sp + 4096 * sw;
             uint64_t nl0 = sl.mask64(pb), nl1 = sl.mask64(pb + 2048);
@@ -401,7 +441,8 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
             }
             const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t t0 = tot & 0xFFFFu;
-            if (lane == 0) s_wsum[(seq & 1u) * kSW + sw] = t0 + (tot >> 16);
+            volatile uint32_t *wsum = s_wsum + (group * 2 + ((seq / kSG) & 1u)) * kSW;
+            if (lane == 0) wsum[sw] = t0 + (tot >> 16);
             if (sw == kSW - 1) {                                      // first newline of the halo: end of the crossing row
                 const int valid = min(max(staged - kTileBytes - 16 * lane, 0), 16);
                 const uint32_t mm = newline_mask16(lds128(sp + kTileBytes + 16 * lane)) & ((1u << valid) - 1u);
@@ -411,11 +452,11 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                 const uint32_t first = __shfl_sync(0xffffffffu, pos, srcl);
                 if (lane == 0) s_desc[slot * kDescWords + kDCross] = b ? first : kNoCross;
             }
-            scan_bar();                                               // warp totals of this tile visible (double-buffered)
+            scan_bar(group);                                          // warp totals of this tile visible (double-buffered)
             uint32_t before = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < kSW; ++w) {
-                const uint32_t v = s_wsum[(seq & 1u) * kSW + w];
+                const uint32_t v = wsum[w];
                 total += v;
                 if (w < sw) before += v;
             }
@@ -432,23 +473,16 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
         }
     } else {
         // ============================ R: rows -> codes -> k-mers -> histogram =================================
-        const int team = warp / kTeamWarps, tw = warp % kTeamWarps;
         const bool cr = a.status[BNPK_ST_CR] != 0;
         const uint64_t hmask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
         const uint64_t kmask = (1ull << (2 * a.k)) - 1;
         const bool fast = hmask && hmask <= 0x3FFFFFFFull;
-        const uint32_t m32x4 = (uint32_t)(hmask & kmask) << 2;       // byte-offset mask into the table
-        const uint32_t hist_sa = smem_addr(s_hist);
+        const int dbg = a.start_offset;                               // development knobs (BNPK_WS_DEBUG), 0 in production
+        const uint32_t m32x4 = (dbg & 1) ? 0u : (uint32_t)(hmask & kmask) << 2;   // byte-offset mask into the table
+        const uint32_t hist_sa = smem_addr(s_hist) + ((dbg & 1) ? 4u * (uint32_t)lane : 0u);
         uint32_t acc_bases = 0, acc_values = 0;                       // per lane: well inside 32 bits for any chunk
-        unsigned long long last_start = 0, last_index = 0;             // 1 + start / entry of the last row this warp counted
+        unsigned long long last_start = 0, last_index = 0;             // 1 + start / entry of the last row this lane counted
         unsigned long long r_complete = 0;
-        const uint32_t sub = (uint32_t)lane & 3u, q = (uint32_t)lane >> 2;
-        const int src1 = (lane & ~3) | (int)((sub + 1u) & 3u), src2 = (lane & ~3) | (int)((sub + 2u) & 3u),
-                  src3 = (lane & ~3) | (int)((sub + 3u) & 3u);
-        const uint32_t cshift = 3u + ls, npc = 1u << cshift;          // newlines per chunk of 8 rows
-        const int src_s = (int)(q << ls);                             // the lane that holds my row's start newline
-        const uint32_t ph = (want + (uint32_t)lane) & pm;             // phase of my newline
-        const bool chk_h = (uint32_t)lane < npc && ph == pm, chk_p = (uint32_t)lane < npc && a.check_plus && ph == 1u;
 
         auto defer_row = [&](uint64_t start, uint64_t r) {
             const unsigned long long d = atomicAdd((unsigned long long *)(a.ws + kWsDeferred), 1ull);
@@ -460,11 +494,21 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
             }
         };
 
-        for (uint32_t seq = (uint32_t)team;; seq += kTeams) {
-            const uint32_t slot = seq & (kNS - 1), par = (seq / kNS) & 1u;
-            mbar_wait(bar_ready + 8 * slot, par);
+        for (uint32_t pops = 0;; ++pops) {
+            // ---- next chunk of this warp
+            volatile uint32_t *qe = s_queue + warp * kQD + (pops & (kQD - 1));
+            uint32_t rec = *qe;
+            while ((rec >> 16) != ((pops + 1u) & 0xFFFFu)) {
+                __nanosleep(200);
+                rec = *qe;
+            }
+            __syncwarp();
+            if (lane == 0) s_qcons[warp] = pops + 1u;
+            __threadfence_block();
+            const uint32_t chunk_id = rec & 0xFFFu;
+            if (chunk_id == kChunkEnd) break;
+            const uint32_t slot = (rec >> 12) & 0xFu;
             const int32_t tile = (int32_t)s_desc[slot * kDescWords + kDTile];
-            if (tile < 0) break;
             const uint32_t tile_nl = s_desc[slot * kDescWords + kDCount];
             const uint32_t crossM = s_desc[slot * kDescWords + kDCross];
             const int64_t line_base = (int64_t)*reinterpret_cast<volatile uint64_t *>(s_desc + slot * kDescWords + kDBase);
@@ -477,40 +521,51 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
             const uint32_t jr0 = (want - base_phase) & pm;
             const int64_t r_first = q0 + ((base_phase + jr0 + 1u) >> ls);
             const int n_rows_tile = (tile_nl > jr0) ? (int)(((tile_nl - 1u - jr0) >> ls) + 1u) : 0;
-            const int n_chunks = (tile_nl > jr0) ? (int)((tile_nl - jr0 + npc - 1u) >> cshift) : 0;
 
-            // one chunk: 8 rows = npc consecutive newlines of the list window that starts at newline index wb
+            // 32 rows, one per lane: rows 32*c .. 32*c+31 of the tile; wb = first newline index held by the list
             auto do_chunk = [&](int c, uint32_t wb) {
-                const uint32_t gi = jr0 + ((uint32_t)c << cshift) + (uint32_t)lane;   // my newline (tile-relative index)
-                uint32_t p = 0xFFFFu;
-                if ((uint32_t)lane < npc && gi < tile_nl) p = list[gi - wb];
-                if ((chk_h || chk_p) && p != 0xFFFFu && byte0 + p + 1 < a.n) {
-                    const uint32_t ch = sp[p + 1];
-                    if (chk_h && ch != a.header_char)
-                        atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], (long long)(q0 + ((base_phase + gi + 1u) >> ls)));
-                    if (chk_p && ch != '+')
-                        atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY], (long long)(q0 + ((base_phase + gi) >> ls)));
-                }
-                const uint32_t ps = __shfl_sync(0xffffffffu, p, src_s), pe = __shfl_sync(0xffffffffu, p, src_s + 1);
-                const int s = 8 * c + (int)q;                         // my row (tile-relative)
-                bool act = ps != 0xFFFFu;
-                int b0 = (int)ps + 1, e = (int)pe;
-                if (act && pe == 0xFFFFu) {                           // the row ends beyond the tile proper
-                    if (crossM != kNoCross) {
+                const int s = 32 * c + lane;                          // my row (tile-relative)
+                bool act = s < n_rows_tile;
+                const uint32_t j = jr0 + ((uint32_t)s << ls);         // the newline before my row
+                int b0 = 0, e = 0;
+                if (act) {
+                    const uint16_t *lp = list + (j - wb);
+                    b0 = (int)lp[0] + 1;
+                    // entry structure (one_line_buffer.py:155-173, fastq_buffer.py:38-45) at the entry's other newlines
+#pragma unroll
+                    for (uint32_t d = 1; d <= 3; ++d) {
+                        if (d <= pm && j + d < tile_nl) {
+                            const uint32_t phase = (want + d) & pm;
+                            const bool chk_h = phase == pm, chk_p = a.check_plus && phase == 1u;
+                            if (chk_h || chk_p) {
+                                const uint32_t p = lp[d];
+                                if (byte0 + p + 1 < a.n) {
+                                    const uint32_t ch = sp[p + 1];
+                                    if (chk_h && ch != a.header_char)
+                                        atomicMin((long long *)&a.status[BNPK_ST_BAD_HEADER_ENTRY], (long long)(q0 + ((base_phase + j + d + 1u) >> ls)));
+                                    if (chk_p && ch != '+')
+                                        atomicMin((long long *)&a.status[BNPK_ST_BAD_PLUS_ENTRY], (long long)(q0 + ((base_phase + j + d) >> ls)));
+                                }
+                            }
+                        }
+                    }
+                    if (j + 1u < tile_nl) {
+                        e = lp[1];
+                    } else if (crossM != kNoCross) {                  // the row ends in the halo
                         e = (int)crossM;
                     } else {                                          // not terminated inside the slot
-                        if (sub == 0 && byte0 + staged < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + s));
+                        if (byte0 + staged < a.n) defer_row(byte0 + b0, (uint64_t)(r_first + s));
                         act = false;                                  // (else: unterminated last line, not an entry)
                     }
-                }
-                if (act && cr && e > b0 && sp[e - 1] == '\r') e -= 1;
-                if (act && e - b0 > kRowMax) {
-                    if (sub == 0) defer_row(byte0 + b0, (uint64_t)(r_first + s));
-                    act = false;
+                    if (act && cr && e > b0 && sp[e - 1] == '\r') e -= 1;
+                    if (act && e - b0 > kRowMax) {
+                        defer_row(byte0 + b0, (uint64_t)(r_first + s));
+                        act = false;
+                    }
                 }
                 const int L = act ? e - b0 : 0;
                 const int npos = max(L - a.k + 1, 0);
-                if (act && sub == 0) {
+                if (act) {
                     acc_bases += (uint32_t)L;
                     acc_values += (uint32_t)npos;
                     if (s == n_rows_tile - 1) {                       // the tile's last counted row (see uncount_kernel)
@@ -518,65 +573,82 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                         last_index = max(last_index, (unsigned long long)(r_first + s) + 1ull);
                     }
                 }
-                const int A0 = b0 >> 4, A1 = (e - 1) >> 4;
+                const int A0 = b0 >> 4;
+                const int nu = L > 0 ? ((e - 1) >> 4) - A0 + 1 : 0;  // 16-byte units my row touches
                 const uint32_t o = (uint32_t)b0 & 15u;
-                const int my_rounds = L > 0 ? ((A1 - A0 + 1) + 3) >> 2 : 0;
-                const int R = __reduce_max_sync(0xffffffffu, my_rounds);
-                auto enc = [&](int r) -> uint32_t {
-                    const int u = A0 + 4 * r + (int)sub;
-                    if (L <= 0 || u > A1) return 0u;
-                    const uint4 qq = lds128(sp + 16 * u);
-                    const int lo = max(b0 - 16 * u, 0), hi = min(e - 16 * u, 16);
+                const int R = __reduce_max_sync(0xffffffffu, nu);
+                const uint8_t *up = sp + 16 * A0;
+
+                uint32_t badacc = 0;                                  // != 0: some byte of my row is outside the alphabet
+                // any unit of my row -> code word (0 beyond the row); only the row's own bytes are validated
+                auto enc_masked = [&](int r) -> uint32_t {
+                    if (r >= nu || (dbg & 4)) return 0u;
+                    const uint4 qq = lds128(up + 16 * r);
+                    const int lo = r == 0 ? (int)o : 0, hi = min(e - 16 * (A0 + r), 16);
                     const uint32_t seq16 = (0xFFFFu >> (16 - hi)) & (0xFFFFu << lo);
                     uint32_t bad;
-                    const uint32_t codes = encode_unit<ENC>(qq, seq16, s_lut, bad);
-                    if (bad) {                                        // rare: exact position, byte by byte
-                        for (int pp = 16 * u + lo; pp < 16 * u + hi; ++pp) {
-                            const uint32_t cc = sp[pp];
-                            bool okb;
-                            if (ENC == BNPK_ENC_CODES) okb = cc < 4;
-                            else if (ENC == BNPK_ENC_LUT) okb = s_lut[cc] < 4;
-                            else { const uint32_t uu = cc | 0x20u; okb = (uu == 'a' || uu == 'c' || uu == 'g' || uu == 't'); }
-                            if (!okb) {
-                                atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE], (long long)(((r_first + s) << 32) | (int64_t)(pp - b0)));
-                                break;
+                    const uint32_t codes = encode_unit<ENC, false>(qq, seq16, s_lut, bad);
+                    badacc |= bad;
+                    return codes;
+                };
+                const uint32_t sh = 2u * o;                           // my row's stream starts at bit 2*o of its first word
+
+                if (fast) {
+                    // A_b = the 16 bases from row position 16b on = funnel(w_b, w_b+1, 2o).  K-mer t of block b is the
+                    // field at bit 2t of (A_b, A_b+1); shifted two bits less, (window & mask) is the table's byte offset.
+                    uint32_t w1 = enc_masked(1);
+                    uint32_t A_cur = __funnelshift_r(enc_masked(0), w1, sh);
+                    int b = 0;
+                    if constexpr (SMEM_HIST) {
+                        // ---- steady state: blocks that are full in every row of the chunk, units that are interior in
+                        // every row.  One straight-line body per block: no votes, no branches, the next unit's load in flight.
+                        const int bfull = __reduce_min_sync(0xffffffffu, nu > 0 ? npos >> 4 : 0x7FFFFFFF);
+                        const int minnu = __reduce_min_sync(0xffffffffu, nu > 0 ? nu : 0x7FFFFFFF);
+                        const int bs = (dbg & 6) ? 0 : min(min(bfull, minnu - 3), R);
+                        // rows that are not there count into a spare word behind the table
+                        const uint32_t mk = nu > 0 ? m32x4 : 0u, dm = nu > 0 ? 0u : (uint32_t)(a.n_bins * 4);
+                        if (bs > 0) {
+                            uint4 qn = lds128(up + 32);
+                            for (; b < bs; ++b) {
+                                const uint4 qq = qn;
+                                qn = lds128(up + 16 * (b + 3));       // inside my row: b + 3 <= minnu - 1
+                                uint32_t bad;
+                                const uint32_t w2 = encode_unit<ENC, true>(qq, 0xFFFFu, s_lut, bad);
+                                badacc |= bad;
+                                const uint32_t A_nxt = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+                                for (int t = 0; t < 16; ++t) {
+                                    const uint32_t win = t == 0 ? A_cur << 2 : __funnelshift_r(A_cur, A_nxt, 2 * t - 2);
+                                    hist_inc(hist_sa + ((win & mk) | dm));
+                                }
+                                A_cur = A_nxt;
+                                w1 = w2;
                             }
                         }
                     }
-                    return codes;
-                };
-                uint32_t c_cur = enc(0);
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t c_nxt = enc(r + 1);
-                    // code words of the next aligned units of my row: lanes of my quad, this round or the next
-                    const uint32_t x1 = __shfl_sync(0xffffffffu, c_cur, src1), y1 = __shfl_sync(0xffffffffu, c_nxt, src1);
-                    const uint32_t x2 = __shfl_sync(0xffffffffu, c_cur, src2), y2 = __shfl_sync(0xffffffffu, c_nxt, src2);
-                    const uint32_t w1 = sub + 1u >= 4u ? y1 : x1, w2 = sub + 2u >= 4u ? y2 : x2;
-                    const int left = npos - 16 * (4 * r + (int)sub);  // k-mers that start in my block of 16 bases
-                    if (fast) {
-                        if (__any_sync(0xffffffffu, left > 0)) {
-                            // stream pre-shifted left by two bits: (window & mask) is the table's byte offset
-                            const bool z = o == 0u;
-                            const uint32_t p0 = z ? 0u : c_cur, p1 = z ? c_cur : w1, p2 = z ? w1 : w2;
-                            const uint32_t sh = (2u * o + 30u) & 31u;
-                            const uint32_t a0 = __funnelshift_r(p0, p1, sh), a1 = __funnelshift_r(p1, p2, sh);
+                    // ---- the rest: masked units, blocks that are not full everywhere
+                    for (; b < R; ++b) {
+                        const uint32_t w2 = enc_masked(b + 2);
+                        const uint32_t A_nxt = __funnelshift_r(w1, w2, sh);
+                        const int left = npos - 16 * b;               // k-mers that start in this block
+                        if (__any_sync(0xffffffffu, left > 0) && !(dbg & 2)) {
                             if constexpr (SMEM_HIST) {
 #pragma unroll
                                 for (int hb = 0; hb < 2; ++hb) {      // two half blocks of eight
                                     if (__all_sync(0xffffffffu, left >= 8 * hb + 8)) {   // every lane has all eight
 #pragma unroll
                                         for (int t = 8 * hb; t < 8 * hb + 8; ++t)
-                                            hist_inc(hist_sa + ((t == 0 ? a0 : __funnelshift_r(a0, a1, 2 * t)) & m32x4));
+                                            hist_inc(hist_sa + ((t == 0 ? A_cur << 2 : __funnelshift_r(A_cur, A_nxt, 2 * t - 2)) & m32x4));
                                     } else if (__any_sync(0xffffffffu, left > 8 * hb)) {
 #pragma unroll
                                         for (int t = 8 * hb; t < 8 * hb + 8; ++t)
-                                            hist_add_val(hist_sa + ((t == 0 ? a0 : __funnelshift_r(a0, a1, 2 * t)) & m32x4), (uint32_t)(t - left) >> 31);
+                                            hist_add_val(hist_sa + ((t == 0 ? A_cur << 2 : __funnelshift_r(A_cur, A_nxt, 2 * t - 2)) & m32x4), (uint32_t)(t - left) >> 31);
                                     }
                                 }
                             } else {
 #pragma unroll
                                 for (int t = 0; t < 16; ++t) {
-                                    const uint32_t v = (t == 0 ? a0 : __funnelshift_r(a0, a1, 2 * t)) & m32x4;
+                                    const uint32_t v = (t == 0 ? A_cur << 2 : __funnelshift_r(A_cur, A_nxt, 2 * t - 2)) & m32x4;
                                     if (t < left) {
                                         if constexpr (HIST == 2) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(a.hist32) + v), 1u);
                                         else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
@@ -584,42 +656,63 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                                 }
                             }
                         }
-                    } else {
-                        const uint32_t x3 = __shfl_sync(0xffffffffu, c_cur, src3), y3 = __shfl_sync(0xffffffffu, c_nxt, src3);
-                        const uint32_t w3 = sub + 3u >= 4u ? y3 : x3;
+                        A_cur = A_nxt;
+                        w1 = w2;
+                    }
+                } else {
+                    // 64-bit hashes (any number of bins): block b reads words b .. b+3
+                    uint32_t w0 = enc_masked(0), w1 = enc_masked(1), w2 = enc_masked(2);
+                    for (int b = 0; b < R; ++b) {
+                        const uint32_t w3 = enc_masked(b + 3);
+                        const int left = npos - 16 * b;
                         if (left > 0) {
-                            const uint32_t sh = 2u * o;
-                            const uint32_t a0 = __funnelshift_r(c_cur, w1, sh), a1 = __funnelshift_r(w1, w2, sh),
+                            const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh),
                                            a2 = __funnelshift_r(w2, w3, sh);
 #pragma unroll 4
                             for (int t = 0; t < 16; ++t) {
                                 if (t < left) {
                                     const uint32_t lo32 = __funnelshift_r(a0, a1, 2 * t), hi32 = __funnelshift_r(a1, a2, 2 * t);
                                     const uint64_t h = (((uint64_t)hi32 << 32) | lo32) & kmask;
-                                    const uint64_t b = hmask ? (h & hmask) : (h % a.n_bins);
-                                    if constexpr (HIST == 2) atomicAdd(a.hist32 + b, 1u);
-                                    else if constexpr (HIST == 1) atomicAdd(s_hist + (uint32_t)b, 1u);
-                                    else atomicAdd(a.hist + b, 1ull);
+                                    const uint64_t bb = hmask ? (h & hmask) : (h % a.n_bins);
+                                    if constexpr (HIST == 2) atomicAdd(a.hist32 + bb, 1u);
+                                    else if constexpr (HIST == 1) atomicAdd(s_hist + (uint32_t)bb, 1u);
+                                    else atomicAdd(a.hist + bb, 1ull);
                                 }
                             }
                         }
+                        w0 = w1;
+                        w1 = w2;
+                        w2 = w3;
                     }
-                    c_cur = c_nxt;
+                }
+                if (badacc) {                                         // rare: exact position of the first bad byte
+                    for (int pp = b0; pp < e; ++pp) {
+                        const uint32_t cc = sp[pp];
+                        bool okb;
+                        if (ENC == BNPK_ENC_CODES) okb = cc < 4;
+                        else if (ENC == BNPK_ENC_LUT) okb = s_lut[cc] < 4;
+                        else { const uint32_t uu = cc | 0x20u; okb = (uu == 'a' || uu == 'c' || uu == 'g' || uu == 't'); }
+                        if (!okb) {
+                            atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE], (long long)(((r_first + s) << 32) | (int64_t)(pp - b0)));
+                            break;
+                        }
+                    }
                 }
             };
 
-            if (tile_nl <= (uint32_t)kNlCap) {
-                // chunks go round the team's warps; the start rotates so that the odd chunk does not always hit the same warp
-                const int first = (tw + kTeamWarps - (int)((seq / kTeams) % kTeamWarps)) % kTeamWarps;
-                for (int c = first; c < n_chunks; c += kTeamWarps) do_chunk(c, 0u);
-            } else if (tw == 0) {
-                // rare: more newlines than the list holds.  One warp walks the tile in windows of the list, which it
+            if (chunk_id == 0u || chunk_id == kChunkWhole)           // the tile's own checks, once per tile
+                tile_head_checks(a, sp, list, tile, tile_nl, (uint64_t)line_base, ls, want, lane, r_complete);
+            if (dbg & 8) {
+            } else if (chunk_id != kChunkWhole) {
+                do_chunk((int)chunk_id, 0u);
+            } else {
+                // rare: more newlines than the list holds.  This warp walks the tile in windows of the list, which it
                 // rebuilds itself from the bytes (window 0 is what the scan warps left).
                 ScanLane sl;
                 sl.init(lane);
-                const int cpw = kWinStep >> cshift;                   // chunks per window
+                const int n_chunks = (n_rows_tile + 31) >> 5, cpw = kWinRows >> 5;   // chunks per window
                 for (int wk = 0; wk * cpw < n_chunks; ++wk) {
-                    const uint32_t wb = (uint32_t)(wk * kWinStep);
+                    const uint32_t wb = (uint32_t)(wk * kWinRows) << ls;
                     if (wk > 0) {
                         __syncwarp();
                         uint32_t running = 0;
@@ -639,17 +732,25 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                         }
                         __syncwarp();
                     }
-                    if (lane == 0) {                                  // last complete entry of the tile, if this window holds it
+                    if (lane == 0 && wk > 0) {                        // last complete entry of the tile, if this window holds it
                         const uint32_t last = tile_nl - 1u;
                         const uint32_t back = (base_phase + last - pm) & pm;
-                        if (last >= back && last - back - wb < (uint32_t)kNlCap && last - back >= wb)
+                        if (last >= back && last - back >= wb && last - back - wb < (uint32_t)kNlCap)
                             r_complete = max(r_complete, (unsigned long long)(byte0 + list[last - back - wb] + 1));
                     }
                     for (int c = wk * cpw; c < min(n_chunks, (wk + 1) * cpw); ++c) do_chunk(c, wb);
                 }
             }
+            // ---- the last chunk of a tile gives its slot back
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_free + 8 * slot);
+            if (lane == 0) {
+                __threadfence_block();
+                const uint32_t old = atomicSub(const_cast<uint32_t *>(s_desc + slot * kDescWords + kDRemain), 1u);
+                if (old == 1u) {
+                    __threadfence_block();
+                    mbar_arrive(bar_free + 8 * slot);
+                }
+            }
         }
         const uint64_t sum_bases = warp_sum_u64(acc_bases), sum_values = warp_sum_u64(acc_values);
 #pragma unroll
@@ -679,13 +780,16 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
 template <int ENC, int HIST>
 static int launch_t(const TileArgs &a, cudaStream_t st) {
     auto kern = tile_ws_kernel<ENC, HIST>;
-    const size_t smem = (size_t)kFixedBytes + (HIST == 1 ? ((a.n_bins * 4 + 127) & ~(uint64_t)127) : 0);
-    BNPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFixedBytes + kMaxBins * 4));
+    const size_t smem = (size_t)kFixedBytes + (HIST == 1 ? ((a.n_bins * 4 + 4 + 127) & ~(uint64_t)127) : 0);
+    BNPK_DYN_SMEM(kern, kFixedBytes + kMaxBins * 4 + 128);
     const int64_t n_tiles = a.tile_end - a.tile_begin;
     if (n_tiles <= 0) return 0;
     const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)sm_count());
+    TileArgs b = a;
+    static const int dbg = [] { const char *e = std::getenv("BNPK_WS_DEBUG"); return e ? atoi(e) : 0; }();
+    b.start_offset = dbg;
     profile_before(st);
-    kern<<<(unsigned)grid, kCta, smem, st>>>(a);
+    kern<<<(unsigned)grid, kCta, smem, st>>>(b);
     profile_after(st);
     BNPK_LAUNCHED("tile_ws_kernel");
     return 0;
