@@ -577,7 +577,7 @@ bool tma_count_eligible(const TileArgs &a, bool smem_hist) {
     if (a.window != 0) return false;                                        // minimizers: register-staged kernel
     if ((reinterpret_cast<uintptr_t>(a.chunk) & 15) != 0) return false;     // bulk copies need 16-byte alignment
     if (smem_hist && a.n_bins > (uint64_t)tma::kMaxBins) return false;
-    if (a.tile_end > 0x7FFFFFF0ll) return false;
+    if (a.tile_end > 0x7FFFFFF0ll || a.n < 16) return false;
     return true;
 }
 
