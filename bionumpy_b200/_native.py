@@ -46,11 +46,15 @@ SIGNATURES = {
     "bnpk_rows_generic_hash": (_i, [_vp, _sz, _vp, _vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "bnpk_rows_minimizers": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "bnpk_rows_kmer_count": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
+    "bnpk_rows_reverse_complement": (_i, [_vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "bnpk_rows_kmer_hash_canonical": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "bnpk_rows_kmer_count_canonical": (_i, [_vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
     "bnpk_bincount": (_i, [_vp, _sz, _i64, _i, _vp, _vp, _vp]),
     "bnpk_bincount_rows": (_i, [_vp, _vp, _sz, _i64, _vp, _vp, _vp]),
     "bnpk_pipeline_create": (_i, [ctypes.POINTER(_vp), _sz, _sz]),
     "bnpk_pipeline_destroy": (None, [_vp]),
     "bnpk_pipeline_kmer_count_host": (_i, [_vp, _vp, _sz, _i, _u8, _i, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp]),
+    "bnpk_pipeline_kmer_count_host_on": (_i, [_vp, _vp, _sz, _i, _u8, _i, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
     "bnpk_synth_fastq": (_i, [_vp, _u64, _u64, _u64, _vp]),
 }
 
@@ -124,11 +128,15 @@ _ws_cache = {}
 
 
 def workspace(n: int, device):
-    """Scratch for the look-back kernels, cached per device and grown on demand."""
+    """Scratch for the look-back kernels: one buffer per (device, stream), grown on demand.  Two streams never
+    share look-back state, and a buffer that is replaced is only freed for the stream that used it (the caching
+    allocator reuses a block on its own stream in order)."""
     need = int(load_library().bnpk_tile_workspace_bytes(n))
-    key = (device.type, device.index)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
+    with torch.cuda.device(device):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream().cuda_stream)
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+            _ws_cache[key] = ws
     return ws

@@ -250,12 +250,22 @@ __device__ __forceinline__ uint64_t warp_sliding_min(uint64_t v, int w) {
     return v;
 }
 
+// min(h, hash of the reverse complement of the k-mer): bases reversed (bit reversal + swap inside each pair) and
+// complemented.  cx = the complement as an XOR on every 2-bit code (ACGT order: 3 -> all ones, ACTG order: 2).
+__device__ __forceinline__ uint64_t canonical_hash(uint64_t h, int k, uint64_t cx) {
+    uint64_t x = __brevll(h ^ cx);
+    x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+    x >>= (64 - 2 * k);
+    return x < h ? x : h;
+}
+
 struct HistTarget {
     unsigned long long *global;  // int64 table in HBM/L2
     uint32_t *smem;              // privatised table (or nullptr)
     uint64_t n_bins;
     uint64_t mask;               // n_bins-1 when n_bins is a power of two, else 0
     unsigned long long delta;    // +1, or -1 for the un-count of an incomplete record
+    uint64_t canon_xor;          // != 0: count min(h, reverse-complement hash) (see canonical_hash)
 };
 
 template <bool SMEM>
@@ -319,7 +329,7 @@ __device__ __forceinline__ uint32_t row_count(const uint32_t *s_codes, int b0, i
     if constexpr (!MINIMIZER) {
         const int npos = L - k + 1;
         // fast path: the bin index only needs the low 32 bits of the window
-        if (ht.mask && ht.mask <= 0xFFFFFFFFull) {
+        if (ht.mask && ht.mask <= 0xFFFFFFFFull && !ht.canon_xor) {
             const uint32_t m32 = (uint32_t)(ht.mask & kmask);
             for (int i = lane; i < npos; i += 32) {
                 const uint32_t lo = stream_lo32(s_codes, (uint32_t)(b0 + i)) & m32;
@@ -329,7 +339,8 @@ __device__ __forceinline__ uint32_t row_count(const uint32_t *s_codes, int b0, i
             }
         } else {
             for (int i = lane; i < npos; i += 32) {
-                const uint64_t h = stream_64(s_codes, (uint32_t)(b0 + i)) & kmask;
+                uint64_t h = stream_64(s_codes, (uint32_t)(b0 + i)) & kmask;
+                if (ht.canon_xor) h = canonical_hash(h, k, ht.canon_xor);
                 hist_add<SMEM_HIST>(ht, h);
                 ++produced;
             }

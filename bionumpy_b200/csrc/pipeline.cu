@@ -15,6 +15,7 @@ struct bnpk_pipeline {
     int64_t *h_status = nullptr;  // pinned
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     std::vector<cudaEvent_t> events;
+    cudaEvent_t ev_in = nullptr;       // the caller's stream at the time of the call
 };
 
 using namespace bnpk;
@@ -41,12 +42,14 @@ int bnpk_pipeline_create(bnpk_pipeline **out, size_t capacity_bytes, size_t slic
     const size_t n_slices = (capacity_bytes + slice_bytes - 1) / slice_bytes;
     p->events.resize(n_slices);
     for (auto &e : p->events) BNPK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    BNPK_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     return 0;
 }
 
 void bnpk_pipeline_destroy(bnpk_pipeline *p) {
     if (!p) return;
     for (auto &e : p->events) cudaEventDestroy(e);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->compute_stream) cudaStreamDestroy(p->compute_stream);
     cudaFree(p->d_chunk);
@@ -57,13 +60,17 @@ void bnpk_pipeline_destroy(bnpk_pipeline *p) {
     delete p;
 }
 
-int bnpk_pipeline_kmer_count_host(bnpk_pipeline *p, const uint8_t *chunk_host, size_t n, int lines_per_entry,
-                                  uint8_t header_char, int check_plus, int trim_cr, int enc_mode,
-                                  const uint8_t *lut256_host, int k, int window_size, int64_t n_bins, int hist_mode,
-                                  int64_t *hist, int64_t *status_host) {
+int bnpk_pipeline_kmer_count_host_on(bnpk_pipeline *p, const uint8_t *chunk_host, size_t n, int lines_per_entry,
+                                     uint8_t header_char, int check_plus, int trim_cr, int enc_mode,
+                                     const uint8_t *lut256_host, int k, int window_size, int64_t n_bins, int hist_mode,
+                                     int64_t *hist, int64_t *status_host, void *stream) {
     if (!p || !chunk_host || !status_host) return set_err(BNPK_E_BADARG, "null argument");
     if (n > p->capacity) return set_err(BNPK_E_BADARG, "chunk larger than the pipeline capacity");
     cudaStream_t cs = p->compute_stream;
+    // the private streams do not synchronise with anybody: order the count after what the caller has queued
+    // (the kernel or memset that produced `hist`)
+    BNPK_CUDA(cudaEventRecord(p->ev_in, (cudaStream_t)stream));
+    BNPK_CUDA(cudaStreamWaitEvent(cs, p->ev_in, 0));
     if (int rc = bnpk_status_init(p->d_status, cs)) return rc;
     if (enc_mode == BNPK_ENC_LUT) {
         if (!lut256_host) return set_err(BNPK_E_BADARG, "lut256 required");
@@ -84,6 +91,14 @@ int bnpk_pipeline_kmer_count_host(bnpk_pipeline *p, const uint8_t *chunk_host, s
     BNPK_CUDA(cudaStreamSynchronize(cs));
     memcpy(status_host, p->h_status, BNPK_ST_WORDS * sizeof(int64_t));
     return 0;
+}
+
+int bnpk_pipeline_kmer_count_host(bnpk_pipeline *p, const uint8_t *chunk_host, size_t n, int lines_per_entry,
+                                  uint8_t header_char, int check_plus, int trim_cr, int enc_mode,
+                                  const uint8_t *lut256_host, int k, int window_size, int64_t n_bins, int hist_mode,
+                                  int64_t *hist, int64_t *status_host) {
+    return bnpk_pipeline_kmer_count_host_on(p, chunk_host, n, lines_per_entry, header_char, check_plus, trim_cr, enc_mode,
+                                            lut256_host, k, window_size, n_bins, hist_mode, hist, status_host, nullptr);
 }
 
 }  // extern "C"

@@ -37,6 +37,7 @@ struct RowArgs {
     const uint64_t *deferred;
     size_t deferred_cap;
     int lpe;
+    uint64_t canon_xor;          // != 0: canonical k-mers (hash / count modes without a minimizer window)
 };
 
 template <int RM, int ENC, bool SMEM_HIST>
@@ -98,7 +99,11 @@ __device__ void warp_row(const RowArgs &a, uint32_t *w_codes, uint32_t *w_flags,
         } else if constexpr (RM == RM_HASH) {
             int64_t *out = reinterpret_cast<int64_t *>(a.out) + out_off + seg_start;
             const int npos = seg_len - span + 1;
-            for (int p = lane; p < npos; p += 32) out[p] = (int64_t)(stream_64(w_codes, (uint32_t)(off + p)) & kmask);
+            for (int p = lane; p < npos; p += 32) {
+                uint64_t h = stream_64(w_codes, (uint32_t)(off + p)) & kmask;
+                if (a.canon_xor) h = canonical_hash(h, a.k, a.canon_xor);
+                out[p] = (int64_t)h;
+            }
             if (npos > 0) acc_values += (uint64_t)((npos - lane + 31) / 32);
         } else if constexpr (RM == RM_MINIMIZER) {
             int64_t *out = reinterpret_cast<int64_t *>(a.out) + out_off + seg_start;
@@ -153,6 +158,7 @@ __global__ void __launch_bounds__(kRowThreads) rows_kernel(const RowArgs a) {
     ht.n_bins = a.n_bins;
     ht.mask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
     ht.delta = 1ull;
+    ht.canon_xor = a.canon_xor;
     __syncthreads();
 
     uint64_t acc_values = 0, acc_bases = 0, acc_long = 0;
@@ -228,6 +234,7 @@ __global__ void uncount_kernel(const RowArgs a) {
     ht.n_bins = a.n_bins;
     ht.mask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
     ht.delta = ~0ull;                                          // -1
+    ht.canon_xor = 0;
     uint64_t produced = 0;
     // the BAD_BASE slot must not be touched by this row: point validation at a scratch word
     RowArgs b = a;
@@ -275,6 +282,23 @@ __global__ void __launch_bounds__(256) rows_generic_hash_kernel(const uint8_t *b
             for (int j = 0; j < k; ++j) h += (unsigned long long)s_lut[base[start + i + j]] * s_pow[j];
             out[o + i] = (int64_t)h;
         }
+    }
+}
+
+// get_reverse_complement (sequence/dna.py:36-65): out row r = lut[row r read backwards]; one warp per row,
+// coalesced writes.  The 256-byte lut is the reference's complement Lookup for the array's encoding.
+__global__ void __launch_bounds__(256) rows_reverse_complement_kernel(const uint8_t *base, const int64_t *starts, const int32_t *lens,
+                                                                      size_t n_rows, const uint8_t *lut, const int64_t *offsets,
+                                                                      uint8_t *out) {
+    __shared__ uint8_t s_lut[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    s_lut[tid] = lut[tid];
+    __syncthreads();
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + tid) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp_global; r < n_rows; r += n_warps) {
+        const int64_t start = starts[r], L = lens[r], o = offsets[r];
+        for (int64_t i = lane; i < L; i += 32) out[o + i] = s_lut[base[start + L - 1 - i]];
     }
 }
 
@@ -420,6 +444,52 @@ int bnpk_rows_kmer_count(const uint8_t *base, size_t base_bytes, const int64_t *
                   : launch_rows_enc<RM_COUNT_MIN, false, false>(a, enc_mode, n_rows, st);
     return sm ? launch_rows_enc<RM_COUNT, true, false>(a, enc_mode, n_rows, st)
               : launch_rows_enc<RM_COUNT, false, false>(a, enc_mode, n_rows, st);
+}
+
+static uint64_t canon_pattern(int complement_xor) {
+    return complement_xor == 3 ? ~0ull : complement_xor == 2 ? 0xAAAAAAAAAAAAAAAAull : 0x5555555555555555ull;
+}
+
+int bnpk_rows_kmer_hash_canonical(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens,
+                                  size_t n_rows, int enc_mode, const uint8_t *lut256, int k, int complement_xor,
+                                  const int64_t *offsets, int64_t *hashes_out, int64_t *status, void *stream) {
+    if (int rc = check_common(enc_mode, lut256, k, 0)) return rc;
+    if (complement_xor < 1 || complement_xor > 3) return set_err(BNPK_E_BADARG, "complement_xor must be 1, 2 or 3");
+    if (n_rows == 0) return 0;
+    RowArgs a{};
+    a.base = base; a.base_bytes = base_bytes; a.starts = starts; a.lens = lens; a.n_rows = n_rows; a.lut = lut256;
+    a.k = k; a.offsets = offsets; a.out = hashes_out; a.n_bins = 1; a.status = status;
+    a.canon_xor = canon_pattern(complement_xor);
+    return launch_rows_enc<RM_HASH, false, false>(a, enc_mode, n_rows, (cudaStream_t)stream);
+}
+
+int bnpk_rows_kmer_count_canonical(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens,
+                                   size_t n_rows, int enc_mode, const uint8_t *lut256, int k, int complement_xor,
+                                   int64_t n_bins, int hist_mode, int64_t *hist, int64_t *status, void *stream) {
+    if (int rc = check_common(enc_mode, lut256, k, 0)) return rc;
+    if (complement_xor < 1 || complement_xor > 3) return set_err(BNPK_E_BADARG, "complement_xor must be 1, 2 or 3");
+    if (n_bins < 1) return set_err(BNPK_E_BINS, "n_bins must be positive");
+    if (hist_mode == BNPK_HIST_SMEM && n_bins > kSmemMaxBins) return set_err(BNPK_E_BINS, "too many bins for the shared-memory histogram");
+    if (n_rows == 0) return 0;
+    RowArgs a{};
+    a.base = base; a.base_bytes = base_bytes; a.starts = starts; a.lens = lens; a.n_rows = n_rows; a.lut = lut256;
+    a.k = k; a.n_bins = (uint64_t)n_bins; a.hist = (unsigned long long *)hist; a.status = status;
+    a.canon_xor = canon_pattern(complement_xor);
+    cudaStream_t st = (cudaStream_t)stream;
+    return use_smem_hist(n_bins, hist_mode) ? launch_rows_enc<RM_COUNT, true, false>(a, enc_mode, n_rows, st)
+                                            : launch_rows_enc<RM_COUNT, false, false>(a, enc_mode, n_rows, st);
+}
+
+int bnpk_rows_reverse_complement(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens,
+                                 size_t n_rows, const uint8_t *lut256, const int64_t *offsets, uint8_t *out, void *stream) {
+    (void)base_bytes;
+    if (!lut256) return set_err(BNPK_E_BADARG, "lut256 required");
+    if (n_rows == 0) return 0;
+    const size_t want = (n_rows + 7) / 8;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(want, (size_t)sm_count() * 8));
+    rows_reverse_complement_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(base, starts, lens, n_rows, lut256, offsets, out);
+    BNPK_LAUNCHED("rows_reverse_complement_kernel");
+    return 0;
 }
 
 }  // extern "C"

@@ -16,6 +16,25 @@ def _need_cuda(t, name="tensor"):
         raise ValueError(f"{name} must be contiguous")
 
 
+def _on_device(fn):
+    """Run an op with the device of its first tensor argument current (kernels launch on the current device's
+    current stream) and check that every tensor argument lives there."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        tensors = [x for x in list(args) + list(kwargs.values()) if isinstance(x, torch.Tensor)]
+        dev = next((t.device for t in tensors if t.is_cuda), None)
+        if dev is None:
+            return fn(*args, **kwargs)
+        for t in tensors:
+            if t.is_cuda and t.device != dev:
+                raise ValueError(f"{fn.__name__}: tensors on different devices ({t.device} and {dev})")
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 class ScanStatus:
     """Host copy of the device status block (bnpk.h BNPK_ST_*)."""
 
@@ -56,6 +75,7 @@ def read_status(status_t) -> ScanStatus:
     return ScanStatus(status_t.cpu().tolist())   # synchronises the stream
 
 
+@_on_device
 def count_byte(chunk, value: int) -> int:
     _need_cuda(chunk, "chunk")
     out = torch.empty(1, dtype=torch.int64, device=chunk.device)
@@ -63,6 +83,7 @@ def count_byte(chunk, value: int) -> int:
     return int(out.item())
 
 
+@_on_device
 def line_split(chunk, lines_per_entry=4, field_line=1, start_offset=0, header_char=ord("@"), check_plus=True,
                trim_cr=-1, max_rows=None):
     """K1.  Returns (starts int64[R'], lens int32[R'], status tensor).  R' = max_rows (default: the
@@ -82,6 +103,7 @@ def line_split(chunk, lines_per_entry=4, field_line=1, start_offset=0, header_ch
     return starts, lens, status
 
 
+@_on_device
 def chunk_kmer_count(chunk, k, n_bins, hist=None, window_size=0, lines_per_entry=4, header_char=ord("@"),
                      check_plus=True, trim_cr=-1, enc_mode=nv.ENC_ASCII_ACGT, lut=None, hist_mode=nv.HIST_AUTO,
                      status=None):
@@ -101,6 +123,7 @@ def chunk_kmer_count(chunk, k, n_bins, hist=None, window_size=0, lines_per_entry
     return hist, status
 
 
+@_on_device
 def row_offsets(lens, shrink=0):
     """int64[R+1] exclusive prefix sums of max(lens - shrink, 0)."""
     _need_cuda(lens, "lens")
@@ -122,6 +145,7 @@ def _rows_args(base, starts, lens):
     return ptr(base), base.numel(), ptr(starts), ptr(lens), lens.numel()
 
 
+@_on_device
 def rows_encode(base, starts, lens, enc_mode, lut=None, offsets=None, status=None):
     if offsets is None:
         offsets = row_offsets(lens, 0)
@@ -134,6 +158,7 @@ def rows_encode(base, starts, lens, enc_mode, lut=None, offsets=None, status=Non
     return out, offsets, status
 
 
+@_on_device
 def rows_kmer_hash(base, starts, lens, enc_mode, k, lut=None, offsets=None, status=None, total=None):
     if offsets is None:
         offsets = row_offsets(lens, k - 1)
@@ -147,6 +172,7 @@ def rows_kmer_hash(base, starts, lens, enc_mode, k, lut=None, offsets=None, stat
     return out, offsets, status
 
 
+@_on_device
 def rows_generic_hash(base, starts, lens, alphabet_size, k, lut=None, offsets=None, status=None):
     """sum_j code[i+j] * alphabet_size^j for alphabets that are not four letters (K3')."""
     if offsets is None:
@@ -160,6 +186,7 @@ def rows_generic_hash(base, starts, lens, alphabet_size, k, lut=None, offsets=No
     return out, offsets, status
 
 
+@_on_device
 def rows_minimizers(base, starts, lens, enc_mode, k, window_size, lut=None, offsets=None, status=None, total=None):
     if offsets is None:
         offsets = row_offsets(lens, window_size - 1)
@@ -173,6 +200,7 @@ def rows_minimizers(base, starts, lens, enc_mode, k, window_size, lut=None, offs
     return out, offsets, status
 
 
+@_on_device
 def rows_kmer_count(base, starts, lens, enc_mode, k, n_bins, window_size=0, lut=None, hist=None,
                     hist_mode=nv.HIST_AUTO, status=None):
     if hist is None:
@@ -184,6 +212,45 @@ def rows_kmer_count(base, starts, lens, enc_mode, k, n_bins, window_size=0, lut=
     return hist, status
 
 
+@_on_device
+@_on_device
+def rows_reverse_complement(base, starts, lens, lut, offsets=None):
+    """get_reverse_complement on a ragged view: out row r = lut[row r backwards] (uint8, contiguous rows)."""
+    if offsets is None:
+        offsets = row_offsets(lens, 0)
+    total = int(offsets[-1].item())
+    out = torch.empty(total, dtype=torch.uint8, device=base.device)
+    check(lib().bnpk_rows_reverse_complement(*_rows_args(base, starts, lens), ptr(lut), ptr(offsets), ptr(out), stream_ptr()))
+    return out, offsets
+
+
+@_on_device
+def rows_kmer_hash_canonical(base, starts, lens, enc_mode, k, complement_xor, lut=None, offsets=None, status=None):
+    """EXTENSION: min(h, hash of the reverse complement) for every k-mer (K3 with a second strand)."""
+    if offsets is None:
+        offsets = row_offsets(lens, k - 1)
+    total = int(offsets[-1].item())
+    out = torch.empty(total, dtype=torch.int64, device=base.device)
+    if status is None:
+        status = nv.new_status(base.device)
+    check(lib().bnpk_rows_kmer_hash_canonical(*_rows_args(base, starts, lens), enc_mode, ptr(lut), k, complement_xor,
+                                              ptr(offsets), ptr(out), ptr(status), stream_ptr()))
+    return out, offsets, status
+
+
+@_on_device
+def rows_kmer_count_canonical(base, starts, lens, enc_mode, k, complement_xor, n_bins, lut=None, hist=None,
+                              hist_mode=nv.HIST_AUTO, status=None):
+    if hist is None:
+        hist = torch.zeros(n_bins, dtype=torch.int64, device=base.device)
+    if status is None:
+        status = nv.new_status(base.device)
+    check(lib().bnpk_rows_kmer_count_canonical(*_rows_args(base, starts, lens), enc_mode, ptr(lut), k, complement_xor,
+                                               n_bins, hist_mode, ptr(hist), ptr(status), stream_ptr()))
+    return hist, status
+
+
+@_on_device
 def bincount(values, n_bins, hist=None, hist_mode=nv.HIST_AUTO, status=None):
     _need_cuda(values, "values")
     if values.dtype != torch.int64:
@@ -196,6 +263,7 @@ def bincount(values, n_bins, hist=None, hist_mode=nv.HIST_AUTO, status=None):
     return hist, status
 
 
+@_on_device
 def bincount_rows(values, offsets, n_bins, status=None):
     _need_cuda(values, "values")
     n_rows = offsets.numel() - 1
@@ -228,10 +296,11 @@ class HostPipeline:
         if chunk_host.is_cuda or chunk_host.dtype != torch.uint8:
             raise TypeError("chunk_host must be a CPU uint8 tensor")
         status = (ctypes.c_int64 * nv.ST_WORDS)()
-        check(lib().bnpk_pipeline_kmer_count_host(
-            self._h, ctypes.c_void_p(chunk_host.data_ptr()), chunk_host.numel(), lines_per_entry, header_char,
-            int(check_plus), trim_cr, enc_mode, ctypes.c_void_p(lut_host.data_ptr()) if lut_host is not None else None,
-            k, window_size, hist.numel(), hist_mode, ptr(hist), ctypes.cast(status, ctypes.c_void_p)))
+        with torch.cuda.device(hist.device):
+            check(lib().bnpk_pipeline_kmer_count_host_on(
+                self._h, ctypes.c_void_p(chunk_host.data_ptr()), chunk_host.numel(), lines_per_entry, header_char,
+                int(check_plus), trim_cr, enc_mode, ctypes.c_void_p(lut_host.data_ptr()) if lut_host is not None else None,
+                k, window_size, hist.numel(), hist_mode, ptr(hist), ctypes.cast(status, ctypes.c_void_p), stream_ptr()))
         return ScanStatus(list(status))
 
     def close(self):

@@ -79,8 +79,13 @@ def _split_long_rows(starts, lens, span, out_offsets=None, piece=LONG_ROW):
 class LazyKmerValues(EncodedRaggedArray):
     """EncodedRaggedArray of k-mer hashes / minimizers whose int64 data appear on first use."""
 
-    def __init__(self, source: _Source, k: int, window_size: int, flat_input: bool = False):
+    def __init__(self, source: _Source, k: int, window_size: int, flat_input: bool = False, canonical: bool = False):
         self._source, self._k, self._window = source, k, window_size
+        self._canonical = canonical
+        if canonical:
+            from .dna import complement_xor_of
+            assert window_size == 0, "canonical minimizers are not implemented"
+            self._cxor = complement_xor_of(source.alphabet_encoding)
         shrink = (window_size if window_size else k) - 1
         self._lens = torch.clamp(source.lens - shrink, min=0).to(torch.int32)
         ends = torch.cumsum(self._lens.to(torch.int64), 0)
@@ -114,6 +119,10 @@ class LazyKmerValues(EncodedRaggedArray):
             if self._window:
                 vals, _, status = ops.rows_minimizers(s.base, p_starts, p_lens, s.enc_mode, self._k, self._window,
                                                       s.lut, p_off, total=total)
+            elif self._canonical:
+                vals, _, status = ops.rows_kmer_hash_canonical(s.base, s.starts, s.lens, s.enc_mode, self._k, self._cxor,
+                                                               s.lut, offsets)
+                p_starts = s.starts
             else:
                 vals, _, status = ops.rows_kmer_hash(s.base, p_starts, p_lens, s.enc_mode, self._k, s.lut, p_off,
                                                      total=total)
@@ -146,6 +155,10 @@ class LazyKmerValues(EncodedRaggedArray):
         if s.alphabet_encoding.alphabet_size != 4:
             hist, _ = ops.bincount(self._data.contiguous(), n_bins)
             return hist
+        if self._canonical:
+            hist, status = ops.rows_kmer_count_canonical(s.base, s.starts, s.lens, s.enc_mode, self._k, self._cxor, n_bins, s.lut)
+            self._check(status)
+            return hist
         buf = s.chunk_buffer
         if buf is not None and buf.can_fuse_count():
             return buf.fused_kmer_histogram(self._k, self._window, n_bins, s.enc_mode, s.lut)
@@ -156,12 +169,13 @@ class LazyKmerValues(EncodedRaggedArray):
         return hist
 
 
-def get_kmers(sequence, k: int):
+def get_kmers(sequence, k: int, canonical: bool = False):
     """kmers.py:36-87.  ``sequence``: EncodedRaggedArray / 1-D EncodedArray, BaseEncoding text or an
-    AlphabetEncoding with four letters; k in 1..31."""
+    AlphabetEncoding with four letters; k in 1..31.  EXTENSION: ``canonical=True`` gives min(hash, hash of the
+    reverse complement) for every k-mer (sequence/dna.py)."""
     assert 0 < k < 32, "k must be larger than 0 and smaller than 32"
     src = _source_of(sequence)
-    out = LazyKmerValues(src, k, 0)
+    out = LazyKmerValues(src, k, 0, canonical=canonical)
     if not config.LAZY:
         out._data
     if isinstance(sequence, EncodedArray):
@@ -175,9 +189,9 @@ def count_kmers(sequence, k: int, axis=None) -> EncodedCounts:
     return count_encoded(get_kmers(sequence, k), axis=axis)
 
 
-def count_kmers_hashed(sequence, k: int, n_buckets: int = 1 << 24, window_size: int = 0) -> torch.Tensor:
+def count_kmers_hashed(sequence, k: int, n_buckets: int = 1 << 24, window_size: int = 0, canonical: bool = False) -> torch.Tensor:
     """EXTENSION: np.bincount(get_kmers(sequence, k) % n_buckets) (or of the minimizers when
     window_size > 0) as an int64 CUDA tensor, fused."""
     assert 0 < k < 32, "k must be larger than 0 and smaller than 32"
     assert window_size == 0 or k <= window_size, "kmer size must be smaller than window size"
-    return count_hashed(LazyKmerValues(_source_of(sequence), k, window_size), n_buckets)
+    return count_hashed(LazyKmerValues(_source_of(sequence), k, window_size, canonical=canonical), n_buckets)

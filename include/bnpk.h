@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BNPK_ABI_VERSION 1
+#define BNPK_ABI_VERSION 2
 
 /* argument errors */
 #define BNPK_E_BADARG   (-1)
@@ -183,6 +183,23 @@ int bnpk_rows_kmer_count(const uint8_t *base, size_t base_bytes, const int64_t *
                          int enc_mode, const uint8_t *lut256, int k, int window_size,
                          int64_t n_bins, int hist_mode, int64_t *hist, int64_t *status, void *stream);
 
+/* get_reverse_complement (sequence/dna.py:36-65: complement Lookup, then every row reversed):
+ *     out[offsets[r] + i] = lut256[base[starts[r] + lens[r] - 1 - i]]; offsets from shrink = 0.  lut256 (device) is
+ *     the complement table of the array's encoding (_get_complement_lookup, sequence/dna.py:13-34). */
+int bnpk_rows_reverse_complement(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens,
+                                 size_t n_rows, const uint8_t *lut256, const int64_t *offsets, uint8_t *out, void *stream);
+
+/* EXTENSION (no reference counterpart; what Jellyfish --canonical does, benchmarks/rules/kmer_counting.smk:11):
+ *     canonical k-mers = min(h, hash of the reverse complement of the same k-mer).  complement_xor is the
+ *     complement as an XOR on a 2-bit code: 3 for "ACGT"-ordered alphabets (DNAEncoding), 2 for "ACTG"-ordered.
+ *     Same outputs as bnpk_rows_kmer_hash / bnpk_rows_kmer_count otherwise. */
+int bnpk_rows_kmer_hash_canonical(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens,
+                                  size_t n_rows, int enc_mode, const uint8_t *lut256, int k, int complement_xor,
+                                  const int64_t *offsets, int64_t *hashes_out, int64_t *status, void *stream);
+int bnpk_rows_kmer_count_canonical(const uint8_t *base, size_t base_bytes, const int64_t *starts, const int32_t *lens,
+                                   size_t n_rows, int enc_mode, const uint8_t *lut256, int k, int complement_xor,
+                                   int64_t n_bins, int hist_mode, int64_t *hist, int64_t *status, void *stream);
+
 /* K5  np.bincount(values % n_bins, minlength=n_bins) accumulated into hist
  *     (sequence/count_encoded.py:173-177; EncodedArray.__array_function__ encoded_array.py:459-460).
  *     Values must be non-negative; n_bins = len(alphabet) reproduces count_encoded exactly
@@ -212,6 +229,12 @@ int  bnpk_pipeline_kmer_count_host(bnpk_pipeline *ctx, const uint8_t *chunk_host
                                    int lines_per_entry, uint8_t header_char, int check_plus, int trim_cr,
                                    int enc_mode, const uint8_t *lut256_host, int k, int window_size,
                                    int64_t n_bins, int hist_mode, int64_t *hist, int64_t *status_host);
+/* The same, ordered after the work already queued on `stream` (whatever produced or zeroed `hist`); the entry point
+ * above orders itself after the legacy default stream. */
+int  bnpk_pipeline_kmer_count_host_on(bnpk_pipeline *ctx, const uint8_t *chunk_host, size_t n,
+                                      int lines_per_entry, uint8_t header_char, int check_plus, int trim_cr,
+                                      int enc_mode, const uint8_t *lut256_host, int k, int window_size,
+                                      int64_t n_bins, int hist_mode, int64_t *hist, int64_t *status_host, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Synthetic workload generator (SURVEY 8d record: "@r%010d\n" + 150 bases + "\n+\n" +

@@ -288,6 +288,48 @@ def get_minimizers_bruteforce(codes_flat, lens, k, window_size):
 # --------------------------------------------------------------------------------------
 # sequence/count_encoded.py:150-188 ; encodings/kmer_encodings.py:55-74
 # --------------------------------------------------------------------------------------
+_COMPLEMENTS = {"A": "T", "G": "C", "C": "G", "T": "A", "N": "N"}
+
+
+def complement_table(alphabet=None) -> np.ndarray:
+    """bionumpy/sequence/dna.py:13-34: the complement Lookup as a table over raw values.  alphabet=None is
+    BaseEncoding (ASCII: only upper-case A, C, G, T, N are known, every other byte maps to 0)."""
+    table = np.zeros(256, dtype=np.uint8)
+    if alphabet is None:
+        for key, value in _COMPLEMENTS.items():
+            table[ord(key)] = ord(value)
+    else:
+        for i, c in enumerate(alphabet):
+            table[i] = alphabet.index(_COMPLEMENTS[c])
+    return table
+
+
+def reverse_complement_rows(flat: np.ndarray, lens: np.ndarray, alphabet=None):
+    """bionumpy/sequence/dna.py:49-65: complement(sequence)[..., ::-1], row by row.  Returns the flat rows."""
+    table = complement_table(alphabet)
+    out = np.empty_like(flat)
+    pos = 0
+    for L in np.asarray(lens, dtype=np.int64):
+        out[pos:pos + L] = table[flat[pos:pos + L]][::-1]
+        pos += L
+    return out
+
+
+def canonical_kmers(codes_flat: np.ndarray, lens: np.ndarray, k: int, alphabet: str = "ACGT"):
+    """EXTENSION (no reference counterpart): min(h_i, hash of the reverse complement of k-mer i), built from the
+    reference's own pieces: get_kmers of the rows and of their reverse complements (k-mer i of a row of length L is
+    k-mer L-k-i of the reverse-complemented row)."""
+    fwd, out_lens = get_kmers(codes_flat, lens, k)
+    rc_rows = reverse_complement_rows(codes_flat, lens, alphabet)
+    rc, _ = get_kmers(rc_rows, lens, k)
+    out = np.empty_like(fwd)
+    pos = 0
+    for n in np.asarray(out_lens, dtype=np.int64):
+        out[pos:pos + n] = np.minimum(fwd[pos:pos + n], rc[pos:pos + n][::-1])
+        pos += n
+    return out, out_lens
+
+
 def count_encoded_flat(values: np.ndarray, n_bins: int) -> np.ndarray:
     """count_encoded(axis=None) (count_encoded.py:167-177): 1 M-element slabs of
     np.bincount(minlength=len(alphabet)) summed.  int64 counts."""

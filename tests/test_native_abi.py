@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/bnpk.h but not exported"
     assert set(names) == set(_native.SIGNATURES), set(names) ^ set(_native.SIGNATURES)
-    assert lib.bnpk_abi_version() == 1
+    assert lib.bnpk_abi_version() == 2
 
 
 def test_header_constants_match_python_mirror():
@@ -54,3 +54,15 @@ def test_compute_fails_loudly_without_gpu():
         bnp.get_kmers(bnp.as_encoded_array("ACGT"), 3)
     with pytest.raises(_native.NativeLibraryError):
         bnp.FastQBuffer.from_raw_buffer(bnp.as_encoded_array("@a\nACGT\n+\n!!!!\n"))
+
+
+def test_torch_library_registers_the_ops():
+    """libbnpk_torch.so (TORCH_LIBRARY(bnpk, ...)) loads without a GPU and registers the dispatcher ops."""
+    import torch
+    from bionumpy_b200 import torch_ops
+    ops = torch_ops.load()
+    for name in ("chunk_kmer_count", "line_split", "row_offsets", "rows_encode", "rows_kmer_hash", "rows_kmer_count",
+                 "rows_reverse_complement", "bincount"):
+        assert hasattr(ops, name), name
+    schema = torch._C._get_schema("bnpk::chunk_kmer_count", "")
+    assert "Tensor(a!) hist" in str(schema)

@@ -247,3 +247,24 @@ def test_synthetic_record_layout():
     seq = o.gather_rows(chunk, starts[:, 1], lens[:, 1])
     counts = np.bincount(seq, minlength=128)[[65, 67, 71, 84]]
     assert counts.sum() == 7500 and counts.min() > 1600                   # roughly uniform ACGT
+
+
+def test_reverse_complement_restatement():
+    """bionumpy/sequence/dna.py:10-65: A<->T, C<->G, N->N on text (other bytes -> 0), codes through the alphabet."""
+    text = np.frombuffer(b"ACGTAACGN", dtype=np.uint8)
+    out = o.reverse_complement_rows(text, np.array([4, 4, 1]))
+    assert out.tobytes() == b"ACGTCGTTN"
+    codes = np.array([0, 1, 2, 3, 0, 0, 1, 2], dtype=np.uint8)            # ACGT AACG in DNAEncoding
+    assert o.reverse_complement_rows(codes, np.array([4, 4]), "ACGT").tolist() == [0, 1, 2, 3, 1, 2, 3, 3]
+    assert o.complement_table("ACTG")[:4].tolist() == [2, 3, 0, 1]
+
+
+def test_canonical_kmers_restatement():
+    """canonical = min(hash, hash of the reverse complement); a palindromic k-mer is its own partner."""
+    codes = o.encode_flat(np.frombuffer(b"ACGTTGCA", dtype=np.uint8), o.alphabet_lut("ACGT"))
+    can, lens = o.canonical_kmers(codes, np.array([8]), 4)
+    fwd, _ = o.get_kmers(codes, np.array([8]), 4)
+    strings = [o.kmer_to_string(int(h), 4) for h in can]
+    assert lens.tolist() == [5] and strings[0] == "ACGT"                  # ACGT is its own reverse complement
+    assert strings[1] == min("CGTT", "AACG", key=lambda s: sum("ACGT".index(c) * 4 ** j for j, c in enumerate(s)))
+    assert all(c <= f for c, f in zip(can, fwd))
