@@ -38,5 +38,12 @@ def bnp_open(filename, mode=None, buffer_type=None, lazy=None):
         suffix = os.path.splitext(base)[1]
     if buffer_type is None:
         buffer_type = _buffer_type_for(suffix)
-    fobj = gzip.open(path, "rb") if is_gzip else open(path, "rb")
-    return NpDataclassReader(CudaFileReader(fobj, buffer_type), lazy)
+    from . import ingest
+    raw = open(path, "rb")
+    reader = ingest.open_reader(path, raw, buffer_type, is_gzip)        # pinned, prefetching ingest (FASTQ / 2-line FASTA)
+    if reader is None:
+        if is_gzip:
+            raw.close()
+            raw = gzip.open(path, "rb")
+        reader = CudaFileReader(raw, buffer_type)
+    return NpDataclassReader(reader, lazy)

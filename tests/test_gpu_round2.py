@@ -135,3 +135,77 @@ def test_two_devices_one_process():
         chunk = torch.from_numpy(host).to(f"cuda:{dev}")
         hist, status = cops.chunk_kmer_count(chunk, 31, 1 << 14)
         assert np.array_equal(hist.cpu().numpy(), want)
+
+
+def test_saccer3_whole_genome_k21(bnp, tmp_path):
+    """BASELINE configs[3] on the reference's own example_data/sacCer3.fa (shipped gzipped under tests/golden):
+    multi-line FASTA -> 17 long rows -> k=21 hashes.  Bucketed histogram (2^24) AND the exact distinct-k-mer table
+    (np.unique) against the oracle."""
+    import gzip
+    import os
+    raw = gzip.open(os.path.join(os.path.dirname(__file__), "golden", "sacCer3.fa.gz")).read()
+    assert len(raw) == 12400379
+    path = tmp_path / "sacCer3.fa"
+    path.write_bytes(raw)
+    # oracle: the reference's multi-line split, encode, hash
+    whole = np.frombuffer((raw if raw.endswith(b"\n") else raw + b"\n") + b">", dtype=np.uint8)
+    size, hs, hl, flat, seq_lens = oracle.multiline_fasta_split(whole)
+    assert seq_lens.size == 17 and int(seq_lens.sum()) == 12157105
+    codes = oracle.encode_flat(flat, oracle.alphabet_lut("ACGT"))
+    want_h, want_lens = oracle.get_kmers(codes, seq_lens, 21)
+    B = 1 << 24
+    want_hist = oracle.count_bucketed_flat(want_h, B)
+    # ours, through bnp.open in chunks and as one buffer
+    hist = torch.zeros(B, dtype=torch.int64, device="cuda")
+    n_entries = 0
+    for chunk in bnp.open(str(path)).read_chunks(min_chunk_size=3_000_000):
+        hist += bnp.count_kmers_hashed(chunk.sequence, 21, B)
+        n_entries += len(chunk)
+    assert n_entries == 17
+    assert np.array_equal(hist.cpu().numpy(), want_hist)
+    chunk = bnp.open(str(path)).read()
+    kmers = bnp.get_kmers(bnp.change_encoding(chunk.sequence, bnp.DNAEncoding), 21)
+    got_h = kmers.raw().ravel().cpu().numpy()
+    assert np.array_equal(kmers._lens.cpu().numpy(), want_lens)
+    u_want, c_want = np.unique(want_h, return_counts=True)
+    u_got, c_got = np.unique(got_h, return_counts=True)
+    assert np.array_equal(u_got, u_want) and np.array_equal(c_got, c_want)
+
+
+def _bgzf(data, block=60000):
+    import struct, zlib
+    out = b""
+    for i in range(0, len(data), block):
+        blk = data[i:i + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        payload = c.compress(blk) + c.flush()
+        out += struct.pack("<BBBBIBBHBBHH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6, 66, 67, 2, len(payload) + 25) + payload + \
+            struct.pack("<II", zlib.crc32(blk), len(blk))
+    return out + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+@pytest.mark.parametrize("kind", ["plain", "gzip", "bgzf"])
+@pytest.mark.parametrize("min_chunk_size", [50_000, 5_000_000])
+def test_open_ingest_paths_count_like_the_oracle(bnp, tmp_path, kind, min_chunk_size):
+    """bnp.open(...).read_chunks() through the pinned / prefetching ingest (io/ingest.py): plain file, ordinary gzip,
+    BGZF -- same chunks as gzip.open + the generic reader would give, same histogram as the oracle."""
+    import gzip
+    rng = np.random.default_rng(21)
+    host = make_fastq(rng, 6000, min_len=1, max_len=260, trailing_newline=(kind != "plain"))
+    data = host.tobytes()
+    path = tmp_path / ("reads.fq" if kind == "plain" else "reads.fq.gz")
+    path.write_bytes(data if kind == "plain" else gzip.compress(data, 4) if kind == "gzip" else _bgzf(data))
+    want, size, n_bases = oracle_hist(np.frombuffer(data if data.endswith(b"\n") else data + b"\n", dtype=np.uint8), 31, 1 << 14)
+    hist = torch.zeros(1 << 14, dtype=torch.int64, device="cuda")
+    n_rec, n_chunks = 0, 0
+    with bnp.open(str(path)) as f:
+        for chunk in f.read_chunks(min_chunk_size=min_chunk_size):
+            hist += bnp.count_kmers_hashed(chunk.sequence, 31, 1 << 14)
+            n_rec += len(chunk)
+            n_chunks += 1
+    assert n_rec == 6000 and np.array_equal(hist.cpu().numpy(), want)
+    assert n_chunks == (1 if min_chunk_size > len(data) else n_chunks) and (min_chunk_size > len(data) or n_chunks > 5)
+    # names and qualities still come out of the chunks (the buffer objects are the ordinary ones)
+    with bnp.open(str(path)) as f:
+        first = f.read_chunk(min_chunk_size=50_000)
+    assert first.sequence[0].to_string() == data.split(b"\n")[1].decode()

@@ -222,3 +222,46 @@ def test_bench_reference_arm_runs_without_gpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "Gbases/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _bgzf(data, block=60000):
+    """A BGZF (bgzip) image of `data`: gzip members with the 'BC' extra field + the empty end-of-file block."""
+    import struct, zlib
+    out = b""
+    for i in range(0, len(data), block):
+        blk = data[i:i + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        payload = c.compress(blk) + c.flush()
+        out += struct.pack("<BBBBIBBHBBHH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6, 66, 67, 2, len(payload) + 25) + payload + \
+            struct.pack("<II", zlib.crc32(blk), len(blk))
+    return out + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def test_ingest_sources_reproduce_the_bytes(tmp_path):
+    """io/ingest.py: the pread source and the gzip sources (ordinary, multi-member, block-parallel BGZF) hand out
+    exactly the requested byte counts, in order -- file.read(n) semantics (bionumpy/io/parser.py:109)."""
+    import gzip
+    from bionumpy_b200.io import ingest
+    rng = np.random.default_rng(0)
+    data = make_fastq(rng, 4000, max_len=300).tobytes()
+
+    def drain(src, n):
+        got, sizes = b"", []
+        while True:
+            buf, k, last = src.finish(src.start(n))
+            got += buf[:k].numpy().tobytes()
+            sizes.append(k)
+            if last:
+                return got, sizes
+    p = tmp_path / "x.fq"
+    p.write_bytes(data)
+    got, sizes = drain(ingest._PreadSource(open(p, "rb")), 100_003)
+    assert got == data and all(s == 100_003 for s in sizes[:-1])
+    for name, blob, parallel in (("a.gz", gzip.compress(data, 5), False), ("b.gz", _bgzf(data), True),
+                                 ("c.gz", gzip.compress(data[:7777]) + gzip.compress(data[7777:]), False)):
+        q = tmp_path / name
+        q.write_bytes(blob)
+        src = ingest._GzipSource(str(q))
+        assert src.parallel == parallel
+        got, sizes = drain(src, 100_003)
+        assert got == data and all(s == 100_003 for s in sizes[:-1]), name
