@@ -19,7 +19,8 @@ from . import encodings, sequence, io, streams
 from .sequence import (get_kmers, get_minimizers, count_encoded, count_kmers, count_hashed, count_kmers_hashed,
                        EncodedCounts, complement, get_reverse_complement)
 from .streams import streamable, bincount, BnpStream
-from .io import bnp_open, FormatException
+from .io import bnp_open, FormatException, IndexedFasta
+from .sequence import KmerIndex, KmerLookup, BloomFilter
 from .io.buffers import CudaFastQBuffer, CudaTwoLineFastaBuffer, FastQBuffer, TwoLineFastaBuffer
 from .io.multiline import CudaMultiLineFastaBuffer, MultiLineFastaBuffer
 from .datatypes import SequenceEntry, SequenceEntryWithQuality

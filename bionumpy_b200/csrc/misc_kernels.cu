@@ -211,6 +211,54 @@ __global__ void __launch_bounds__(256) bincount_rows_kernel(const int64_t *value
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Indexed FASTA (io/indexed_fasta.py:101-206): sequence positions -> file bytes, skipping the line ends.
+// Row r = bases [row_start[r], row_start[r] + row_len[r]) of the contig whose first base is file byte
+// contig_offset[r], written with lenc[r] bases per line of lenb[r] bytes.  One warp per row, coalesced writes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fasta_gather_kernel(const uint8_t *file, size_t file_bytes, size_t n_rows,
+                                                           const int64_t *contig_offset, const int64_t *row_start,
+                                                           const int64_t *row_len, const int32_t *lenc, const int32_t *lenb,
+                                                           const int64_t *out_offsets, uint8_t *out, int64_t *status) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp_global; r < n_rows; r += n_warps) {
+        const int64_t base = contig_offset[r], s = row_start[r], L = row_len[r], o = out_offsets[r];
+        const int64_t c = lenc[r], b = lenb[r];
+        for (int64_t i = lane; i < L; i += 32) {
+            const int64_t p = s + i;
+            const int64_t byte = base + (p / c) * b + p % c;
+            uint8_t v = 0;
+            if (byte >= 0 && (size_t)byte < file_bytes) v = file[byte];
+            else atomicMin((long long *)&status[BNPK_ST_BAD_BASE], (long long)(((int64_t)r << 32) | i));
+            out[o + i] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bloom filter over k-mer hashes (sequence/bloom_filter.py:15-42): bit j of the filter is the byte mask[j];
+// hash function i is v ^ offsets[i], reduced mod the mask size.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bloom_insert_kernel(const int64_t *values, size_t n, const int64_t *offsets, int n_hash,
+                                                           uint8_t *mask, uint64_t mask_size) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int64_t v = values[i];
+        for (int h = 0; h < n_hash; ++h) mask[(uint64_t)(v ^ offsets[h]) % mask_size] = 1;
+    }
+}
+__global__ void __launch_bounds__(256) bloom_query_kernel(const int64_t *values, size_t n, const int64_t *offsets, int n_hash,
+                                                          const uint8_t *mask, uint64_t mask_size, uint8_t *out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int64_t v = values[i];
+        uint8_t all = 1;
+        for (int h = 0; h < n_hash; ++h) all &= mask[(uint64_t)(v ^ offsets[h]) % mask_size];
+        out[i] = all;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // synthetic FASTQ (bit-identical to oracle/bnp_oracle.py:synthetic_fastq)
 // ------------------------------------------------------------------------------------------
@@ -374,6 +422,38 @@ int bnpk_bincount_rows(const int64_t *values, const int64_t *offsets, size_t n_r
     bincount_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(values, offsets, n_rows, (uint64_t)n_bins,
                                                                  (unsigned long long *)out, status);
     BNPK_LAUNCHED("bincount_rows_kernel");
+    return 0;
+}
+
+int bnpk_fasta_gather(const uint8_t *file, size_t file_bytes, size_t n_rows, const int64_t *contig_offset,
+                      const int64_t *row_start, const int64_t *row_len, const int32_t *lenc, const int32_t *lenb,
+                      const int64_t *out_offsets, uint8_t *out, int64_t *status, void *stream) {
+    if (n_rows == 0) return 0;
+    const size_t want = (n_rows + 7) / 8;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(want, (size_t)sm_count() * 8));
+    fasta_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(file, file_bytes, n_rows, contig_offset, row_start, row_len, lenc,
+                                                                lenb, out_offsets, out, status);
+    BNPK_LAUNCHED("fasta_gather_kernel");
+    return 0;
+}
+
+int bnpk_bloom_insert(const int64_t *values, size_t n, const int64_t *offsets, int n_hash, uint8_t *mask, size_t mask_size,
+                      void *stream) {
+    if (n_hash < 1 || mask_size == 0) return set_err(BNPK_E_BADARG, "bloom filter needs hash functions and a mask");
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16));
+    bloom_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(values, n, offsets, n_hash, mask, (uint64_t)mask_size);
+    BNPK_LAUNCHED("bloom_insert_kernel");
+    return 0;
+}
+
+int bnpk_bloom_query(const int64_t *values, size_t n, const int64_t *offsets, int n_hash, const uint8_t *mask, size_t mask_size,
+                     uint8_t *out, void *stream) {
+    if (n_hash < 1 || mask_size == 0) return set_err(BNPK_E_BADARG, "bloom filter needs hash functions and a mask");
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16));
+    bloom_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(values, n, offsets, n_hash, mask, (uint64_t)mask_size, out);
+    BNPK_LAUNCHED("bloom_query_kernel");
     return 0;
 }
 

@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                     uint32_t w1 = enc_masked(1);
                     uint32_t A_cur = __funnelshift_r(enc_masked(0), w1, sh);
                     int b = 0;
-                    if constexpr (SMEM_HIST) {
+                    {
                         // ---- steady state: blocks that are full in every row of the chunk, units that are interior in
                         // every row.  One straight-line body per block: no votes, no branches, the next unit's load in flight.
                         const int bfull = __reduce_min_sync(0xffffffffu, nu > 0 ? npos >> 4 : 0x7FFFFFFF);
@@ -641,10 +641,19 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                                 const uint32_t w2 = encode_unit<ENC, true>(qq, 0xFFFFu, s_lut, bad);
                                 badacc |= bad;
                                 const uint32_t A_nxt = __funnelshift_r(w1, w2, sh);
+                                if constexpr (SMEM_HIST) {
 #pragma unroll
-                                for (int t = 0; t < 16; ++t) {
-                                    const uint32_t win = t == 0 ? A_cur << 2 : __funnelshift_r(A_cur, A_nxt, 2 * t - 2);
-                                    hist_inc(hist_sa + ((win & mk) | dm));
+                                    for (int t = 0; t < 16; ++t) {
+                                        const uint32_t win = t == 0 ? A_cur << 2 : __funnelshift_r(A_cur, A_nxt, 2 * t - 2);
+                                        hist_inc(hist_sa + ((win & mk) | dm));
+                                    }
+                                } else if (nu > 0) {                  // global table: one RED per k-mer, no per-k-mer test
+#pragma unroll
+                                    for (int t = 0; t < 16; ++t) {
+                                        const uint32_t v = (t == 0 ? A_cur << 2 : __funnelshift_r(A_cur, A_nxt, 2 * t - 2)) & m32x4;
+                                        if constexpr (HIST == 2) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(a.hist32) + v), 1u);
+                                        else atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(a.hist) + 2 * (size_t)v), 1ull);
+                                    }
                                 }
                                 A_cur = A_nxt;
                                 w1 = w2;

@@ -213,6 +213,24 @@ int bnpk_bincount_rows(const int64_t *values, const int64_t *offsets, size_t n_r
                        int64_t *out, int64_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Indexed FASTA (io/indexed_fasta.py:101-206, IndexedFasta.__getitem__ / get_interval_sequences): rows of bases out of
+ * a device-resident FASTA file image, line ends skipped.  Row r = bases [row_start[r], row_start[r] + row_len[r]) of
+ * the contig whose first base is file byte contig_offset[r] (.fai column 3), lenc[r] bases per line of lenb[r] bytes
+ * (.fai columns 4, 5).  out[out_offsets[r] + i]; a position outside the file is reported in status[BNPK_ST_BAD_BASE].
+ * ------------------------------------------------------------------------------------- */
+int bnpk_fasta_gather(const uint8_t *file, size_t file_bytes, size_t n_rows, const int64_t *contig_offset,
+                      const int64_t *row_start, const int64_t *row_len, const int32_t *lenc, const int32_t *lenb,
+                      const int64_t *out_offsets, uint8_t *out, int64_t *status, void *stream);
+
+/* Bloom filter over k-mer hashes (sequence/bloom_filter.py:15-42): hash function i is v ^ offsets[i]; the filter is
+ * one byte per position (the reference's bool mask).  insert: mask[(v ^ offsets[i]) % mask_size] = 1 for every value and
+ * function; query: out[j] = AND over the functions. */
+int bnpk_bloom_insert(const int64_t *values, size_t n, const int64_t *offsets, int n_hash, uint8_t *mask, size_t mask_size,
+                      void *stream);
+int bnpk_bloom_query(const int64_t *values, size_t n, const int64_t *offsets, int n_hash, const uint8_t *mask, size_t mask_size,
+                     uint8_t *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer entry point (end-to-end): the call a reader loop makes with a chunk that is
  * still in host memory.  Copies `chunk_host` (pinned or pageable) to the device in slices on
  * a private copy stream, overlapping each slice's H2D with the fused count of the previous

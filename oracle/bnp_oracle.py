@@ -330,6 +330,67 @@ def canonical_kmers(codes_flat: np.ndarray, lens: np.ndarray, k: int, alphabet: 
     return out, out_lens
 
 
+def fasta_index(data: np.ndarray) -> dict:
+    """bionumpy/io/indexed_fasta.py:34-58 + FastaIdxBuffer (io/multiline_buffer.py:112-157): per contig the sequence
+    length, the file offset of its first base, bases per line (lenc) and bytes per line (lenb) -- the .fai columns."""
+    text = bytes(data).decode("latin1")
+    out, pos, name, cur = {}, 0, None, None
+    for line in text.split("\n"):
+        raw_len = len(line) + 1
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            cur = out[name] = {"rlen": 0, "offset": pos + raw_len, "lenc": 0, "lenb": 0}
+        elif cur is not None and line != "":
+            body = line.rstrip("\r")
+            if cur["lenc"] == 0:
+                cur["lenc"], cur["lenb"] = len(body), raw_len
+            cur["rlen"] += len(body)
+        pos += raw_len
+    return out
+
+
+def indexed_fasta_interval(data: np.ndarray, idx: dict, start: int, stop: int) -> np.ndarray:
+    """IndexedFasta.get_interval_sequences for one interval (io/indexed_fasta.py:180-200): read the byte range, delete
+    the line-end bytes."""
+    lenb, lenc = idx["lenb"], idx["lenc"]
+    start_row, start_mod = start // lenc, start % lenc
+    start_offset = start_row * lenb + start_mod
+    stop_row = stop // lenc
+    stop_offset = stop_row * lenb + stop % lenc
+    tmp = data[idx["offset"] + start_offset: idx["offset"] + stop_offset]
+    drop = []
+    for j in range(stop_row - start_row):
+        first = lenb * (j + 1) - start_mod - (lenb - lenc)            # every byte of the line end (1 or 2 with \r\n)
+        drop.extend(range(first, first + (lenb - lenc)))
+    return np.delete(tmp, [d for d in drop if d < tmp.size])
+
+
+def bloom_filter_mask(values: np.ndarray, offsets, mask_size: int) -> np.ndarray:
+    """bionumpy/sequence/bloom_filter.py:21-39: insert."""
+    mask = np.zeros(mask_size, dtype=bool)
+    for off in offsets:
+        mask[(np.asarray(values, dtype=np.int64) ^ np.int64(off)) % mask_size] = True
+    return mask
+
+
+def bloom_filter_query(mask: np.ndarray, values: np.ndarray, offsets) -> np.ndarray:
+    """bionumpy/sequence/bloom_filter.py:41-42."""
+    out = np.ones(np.shape(values), dtype=bool)
+    for off in offsets:
+        out &= mask[(np.asarray(values, dtype=np.int64) ^ np.int64(off)) % mask.size]
+    return out
+
+
+def kmer_index(hashes_flat: np.ndarray, lens: np.ndarray) -> dict:
+    """bionumpy/sequence/indexing/kmer_indexing.py:24-46: k-mer hash -> sorted indices of the rows that contain it."""
+    out, pos = {}, 0
+    for r, n in enumerate(np.asarray(lens, dtype=np.int64)):
+        for h in set(int(x) for x in hashes_flat[pos:pos + n]):
+            out.setdefault(h, []).append(r)
+        pos += n
+    return out
+
+
 def count_encoded_flat(values: np.ndarray, n_bins: int) -> np.ndarray:
     """count_encoded(axis=None) (count_encoded.py:167-177): 1 M-element slabs of
     np.bincount(minlength=len(alphabet)) summed.  int64 counts."""

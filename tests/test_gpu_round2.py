@@ -209,3 +209,72 @@ def test_open_ingest_paths_count_like_the_oracle(bnp, tmp_path, kind, min_chunk_
     with bnp.open(str(path)) as f:
         first = f.read_chunk(min_chunk_size=50_000)
     assert first.sequence[0].to_string() == data.split(b"\n")[1].decode()
+
+
+def test_indexed_fasta_on_saccer3(bnp, tmp_path):
+    """io/indexed_fasta.py:61-206 on the reference's own sacCer3.fa: contig lengths, a whole contig, random intervals
+    (line ends skipped on the device) against the oracle's restatement; k-mers of the intervals."""
+    import gzip
+    import os
+    raw = gzip.open(os.path.join(os.path.dirname(__file__), "golden", "sacCer3.fa.gz")).read()
+    path = tmp_path / "sacCer3.fa"
+    path.write_bytes(raw)
+    data = np.frombuffer(raw, dtype=np.uint8)
+    idx = oracle.fasta_index(data)
+    fa = bnp.IndexedFasta(str(path))
+    assert fa.get_contig_lengths() == {k: v["rlen"] for k, v in idx.items()} and len(idx) == 17
+    assert sum(fa.get_contig_lengths().values()) == 12157105
+    chrom = fa["chrIII"]
+    assert chrom.raw().cpu().numpy().tobytes() == oracle.indexed_fasta_interval(data, idx["chrIII"], 0, idx["chrIII"]["rlen"]).tobytes()
+    rng = np.random.default_rng(2)
+    names = [c for c in idx if c != "chrM"]      # chrM ends with two short lines: outside what a .fai can describe
+    iv = []
+    for _ in range(200):
+        c = names[int(rng.integers(len(names)))]
+        a = int(rng.integers(0, idx[c]["rlen"] - 1))
+        b = int(min(idx[c]["rlen"], a + rng.integers(1, 5000)))
+        iv.append((c, a, b))
+    iv.append(("chrI", 0, 50))
+    iv.append(("chrI", 49, 51))
+    seqs = fa.get_interval_sequences(iv)
+    flat = seqs.ravel().raw().cpu().numpy()
+    pos = 0
+    for c, a, b in iv:
+        want = oracle.indexed_fasta_interval(data, idx[c], a, b)
+        assert want.size == b - a and np.array_equal(flat[pos:pos + b - a], want), (c, a, b)
+        pos += b - a
+    # the intervals go straight into the k-mer path
+    upper = bnp.EncodedRaggedArray(bnp.EncodedArray(seqs.ravel().raw(), bnp.BaseEncoding), seqs._lens)
+    hist = bnp.count_kmers_hashed(upper, 21, 1 << 16)
+    codes = oracle.encode_flat(flat, oracle.alphabet_lut("ACGT"))
+    h, _ = oracle.get_kmers(codes, np.array([b - a for _, a, b in iv]), 21)
+    assert np.array_equal(hist.cpu().numpy(), oracle.count_bucketed_flat(h, 1 << 16))
+
+
+def test_kmer_index_and_bloom_filter(bnp):
+    """sequence/indexing/kmer_indexing.py:24-55 and sequence/bloom_filter.py:21-42 against the oracle."""
+    rng = np.random.default_rng(17)
+    flat, lens = _rows(rng, 400, max_len=60)
+    ragged = bnp.EncodedRaggedArray(bnp.EncodedArray(torch.from_numpy(flat).cuda(), bnp.DNAEncoding), lens)
+    k = 5
+    h, hl = oracle.get_kmers(flat, lens, k)
+    want = oracle.kmer_index(h, hl)
+    index = bnp.KmerIndex.create_index(ragged, k)
+    for key in list(want)[:200] + [int(h[0])]:
+        assert index.get_indices(key).cpu().tolist() == want[key]
+    assert index.get_indices("ACGTA").cpu().tolist() == want.get(sum("ACGT".index(c) * 4 ** j for j, c in enumerate("ACGTA")), [])
+    lookup = bnp.KmerLookup.from_sequences(ragged, k)
+    some = next(iter(want))
+    assert len(lookup.get_sequences(some)) == len(want[some])
+    # Bloom filter
+    kmers = bnp.get_kmers(ragged, 21)
+    hv, _ = oracle.get_kmers(flat, lens, 21)
+    offsets = np.random.RandomState(12345).randint(0, 100003, 3)
+    bf = bnp.BloomFilter.from_m_and_k(100003, 3)
+    bf.insert(kmers)
+    mask = oracle.bloom_filter_mask(hv, offsets, 100003)
+    assert np.array_equal(bf._mask.cpu().numpy().astype(bool), mask)
+    probe = rng.integers(0, 1 << 42, size=5000)
+    got = bf[torch.from_numpy(probe).cuda()].cpu().numpy()
+    assert np.array_equal(got, oracle.bloom_filter_query(mask, probe, offsets))
+    assert bool(bf[kmers.raw().ravel()].all().item())

@@ -268,3 +268,32 @@ def test_canonical_kmers_restatement():
     assert lens.tolist() == [5] and strings[0] == "ACGT"                  # ACGT is its own reverse complement
     assert strings[1] == min("CGTT", "AACG", key=lambda s: sum("ACGT".index(c) * 4 ** j for j, c in enumerate(s)))
     assert all(c <= f for c, f in zip(can, fwd))
+
+
+def test_fasta_index_restatement_and_host_create_index(tmp_path):
+    """The .fai columns (indexed_fasta.py:13-58) on a small file with a short last line and a one-line contig; the
+    product's host-side create_index must agree with the oracle's restatement."""
+    text = b">chr1 first\nACGTACGTAC\nGGGTTTAAAC\nACG\n>chr2\nTTTT\n>empty\n>chr3 x y\nAC\nGT\n"
+    data = np.frombuffer(text, dtype=np.uint8)
+    idx = o.fasta_index(data)
+    assert idx["chr1"] == {"rlen": 23, "offset": 12, "lenc": 10, "lenb": 11}
+    assert idx["chr2"] == {"rlen": 4, "offset": 44, "lenc": 4, "lenb": 5}
+    assert idx["chr3"]["rlen"] == 4 and idx["chr3"]["lenc"] == 2
+    assert o.indexed_fasta_interval(data, idx["chr1"], 8, 23).tobytes() == b"ACGGGTTTAAACACG"
+    assert o.indexed_fasta_interval(data, idx["chr1"], 0, 10).tobytes() == b"ACGTACGTAC"
+    p = tmp_path / "small.fa"
+    p.write_bytes(text)
+    from bionumpy_b200.io.indexed_fasta import create_index
+    got = create_index(p)
+    for name in ("chr1", "chr2", "chr3"):
+        assert got[name] == idx[name], (name, got[name], idx[name])
+    assert got["empty"]["rlen"] == 0
+
+
+def test_bloom_and_kmer_index_restatements():
+    vals = np.array([5, 9, 1 << 40, 77], dtype=np.int64)
+    mask = o.bloom_filter_mask(vals, [3, 1000], 101)
+    assert o.bloom_filter_query(mask, vals, [3, 1000]).all() and mask.sum() <= 8
+    assert not o.bloom_filter_query(mask, np.array([6]), [3, 1000])[0] or mask[(6 ^ 3) % 101]
+    idx = o.kmer_index(np.array([1, 2, 1, 3, 1]), np.array([3, 2]))
+    assert idx == {1: [0, 1], 2: [0], 3: [1]}
