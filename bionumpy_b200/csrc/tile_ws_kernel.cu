@@ -27,7 +27,7 @@
 namespace bnpk {
 namespace ws {
 
-constexpr int kNS = 8;                          // ring slots
+constexpr int kNS = 8;                          // ring slots (a ninth, paid for with a shorter newline list, did not help)
 constexpr int kHalo = 512;
 constexpr int kSlot = kTileBytes + kHalo;
 constexpr int kNlCap = 1024;                    // newline positions of one tile kept in shared memory
@@ -47,7 +47,7 @@ constexpr int kWarps = kFWarp + 1;
 constexpr int kCta = kWarps * 32;
 constexpr int kFK = 6;                          // look-back loads per lane kept in flight (192 tiles)
 static_assert(kSW * 4096 == kTileBytes, "scan geometry");
-static_assert((kNS & (kNS - 1)) == 0 && (kQN & (kQN - 1)) == 0 && kRW <= 32, "ring sizes");
+static_assert(kNS <= 15 && (kQN & (kQN - 1)) == 0 && kRW <= 32, "ring sizes");
 static_assert(kWinRows % 32 == 0 && 4 * kWinRows + 64 <= kNlCap, "list window");
 
 // per-slot descriptor (32-bit words)
@@ -66,10 +66,10 @@ constexpr uint32_t kChunkEnd = 0xFFEu;
 constexpr int kOffSlots = 0;
 constexpr int kOffList = kOffSlots + kNS * kSlot;
 constexpr int kOffDesc = kOffList + kNS * kNlCap * 2;
-constexpr int kOffBar = kOffDesc + kNS * kDescWords * 4;      // full | scanned | free, kNS each
+constexpr int kOffBar = (kOffDesc + kNS * kDescWords * 4 + 7) & ~7;   // full | scanned | free, kNS each
 constexpr int kOffWsum = kOffBar + 3 * kNS * 8;               // [group][2][kSW]
 constexpr int kOffQueue = kOffWsum + kSG * 2 * kSW * 4;       // [kQN] entries, then the head counter
-constexpr int kOffLut = kOffQueue + kQN * 4 + 16;
+constexpr int kOffLut = (kOffQueue + kQN * 4 + 16 + 15) & ~15;
 constexpr int kFixedBytes = kOffLut + 256;
 static_assert(kOffBar % 8 == 0 && kOffLut % 16 == 0, "alignment");
 
@@ -183,6 +183,20 @@ __device__ __forceinline__ void emit_positions(uint64_t m, uint32_t li, uint32_t
         hi &= hi - 1;
         if (li - wb < (uint32_t)kNlCap) list[li - wb] = (uint16_t)(pos + 32 + bit);
         ++li;
+    }
+}
+
+// The scan warps' version for both pieces of a lane at once: four independent bit chains (low and high half of
+// each 64-bit mask) advance together, so the latency of the bit searches (XU pipe) overlaps instead of adding up.
+__device__ __forceinline__ void emit_positions2(uint64_t m0, uint32_t li0, uint32_t pos0, uint64_t m1, uint32_t li1, uint32_t pos1,
+                                                uint16_t *list) {
+    uint32_t a = (uint32_t)m0, b = (uint32_t)(m0 >> 32), c = (uint32_t)m1, d = (uint32_t)(m1 >> 32);
+    uint32_t ia = li0, ib = li0 + (uint32_t)__popc(a), ic = li1, id = li1 + (uint32_t)__popc(c);
+    while (a | b | c | d) {
+        if (a) { const uint32_t l = a & (0u - a); a ^= l; if (ia < (uint32_t)kNlCap) list[ia] = (uint16_t)(pos0 + __popc(l - 1u)); ++ia; }
+        if (b) { const uint32_t l = b & (0u - b); b ^= l; if (ib < (uint32_t)kNlCap) list[ib] = (uint16_t)(pos0 + 32u + __popc(l - 1u)); ++ib; }
+        if (c) { const uint32_t l = c & (0u - c); c ^= l; if (ic < (uint32_t)kNlCap) list[ic] = (uint16_t)(pos1 + __popc(l - 1u)); ++ic; }
+        if (d) { const uint32_t l = d & (0u - d); d ^= l; if (id < (uint32_t)kNlCap) list[id] = (uint16_t)(pos1 + 32u + __popc(l - 1u)); ++id; }
     }
 }
 
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
         if (lane == 0) {
             int nend = 0;
             for (uint32_t seq = 0;; ++seq) {
-                const uint32_t slot = seq & (kNS - 1), use = seq / kNS;
+                const uint32_t slot = seq % kNS, use = seq / kNS;
                 const uint32_t tw0 = (uint32_t)clock64();
                 if (use > 0) mbar_wait_free(bar_free + 8 * slot, (use - 1u) & 1u);
                 if (a.start_offset & 16) {
@@ -344,9 +358,10 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
         unsigned long long f_complete = 0;
         uint32_t pushes = 0;                                         // chunks queued so far (uniform)
         auto push = [&](uint32_t idx, uint32_t rec) {                // one lane per record
-            volatile uint32_t *qe = s_queue + (idx & (kQN - 1));
-            while (*qe != 0u) __nanosleep(64);                       // the entry's previous chunk has not been taken yet
-            *qe = (((idx & 0x7FFFu) + 1u) << 16) | rec;
+            // (queue words are only touched with atomics: a one-word message protocol, clean under racecheck)
+            uint32_t *qe = const_cast<uint32_t *>(s_queue) + (idx & (kQN - 1));
+            while (atomicOr(qe, 0u) != 0u) __nanosleep(64);          // the entry's previous chunk has not been taken yet
+            atomicExch(qe, (((idx & 0x7FFFu) + 1u) << 16) | rec);
         };
         auto issue = [&](uint64_t *v, int64_t lo, int64_t hi) {      // counts of the tiles lo+1 .. hi-1
 #pragma unroll
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
         uint64_t vC[kFK];
         issue(vC, prev, tile);
         for (uint32_t seq = 0; tile < (int64_t)tile_end; ++seq) {
-            const uint32_t slot = seq & (kNS - 1), par = (seq / kNS) & 1u;
+            const uint32_t slot = seq % kNS, par = (seq / kNS) & 1u;
             uint64_t vN[kFK];
             issue(vN, tile, tile + G);                                // the next tile's, a tile period ahead
             uint32_t sum32 = 0;
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
         ScanLane sl;
         sl.init(lane);
         for (uint32_t seq = (uint32_t)group;; seq += kSG) {
-            const uint32_t slot = seq & (kNS - 1), par = (seq / kNS) & 1u;
+            const uint32_t slot = seq % kNS, par = (seq / kNS) & 1u;
             mbar_wait_full_s(bar_full + 8 * slot, par);
             const int32_t tile = (int32_t)s_desc[slot * kDescWords + kDTile];
             if (tile < 0) break;
@@ -474,8 +489,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
             }
             uint16_t *list = s_list + slot * kNlCap;
             const uint32_t pos0 = 4096u * (uint32_t)sw + 64u * (uint32_t)lane;
-            emit_positions(nl0, before + (inc & 0xFFFFu) - cnt0, pos0, list, 0u);
-            emit_positions(nl1, before + t0 + (inc >> 16) - cnt1, pos0 + 2048u, list, 0u);
+            emit_positions2(nl0, before + (inc & 0xFFFFu) - cnt0, pos0, nl1, before + t0 + (inc >> 16) - cnt1, pos0 + 2048u, list);
             if ((a.start_offset & 16) && sw == 0 && lane == 0) s_desc[slot * kDescWords + kDTScanned] = (uint32_t)clock64();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_scanned + 8 * slot);
@@ -508,14 +522,17 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
             uint32_t idx = 0;
             if (lane == 0) idx = atomicAdd(s_qhead, 1u);
             idx = __shfl_sync(0xffffffffu, idx, 0);
-            volatile uint32_t *qe = s_queue + (idx & (kQN - 1));
-            uint32_t rec = *qe;
-            while ((rec >> 16) != (idx & 0x7FFFu) + 1u) {
-                __nanosleep(100);
-                rec = *qe;
+            uint32_t *qe = const_cast<uint32_t *>(s_queue) + (idx & (kQN - 1));
+            uint32_t rec = 0;
+            if (lane == 0) {
+                rec = atomicOr(qe, 0u);
+                while ((rec >> 16) != (idx & 0x7FFFu) + 1u) {
+                    __nanosleep(100);
+                    rec = atomicOr(qe, 0u);
+                }
+                atomicExch(qe, 0u);                                   // taken
             }
-            __syncwarp();
-            if (lane == 0) *qe = 0u;                                  // taken
+            rec = __shfl_sync(0xffffffffu, rec, 0);
             __threadfence_block();
             const uint32_t chunk_id = rec & 0xFFFu;
             if (chunk_id == kChunkEnd) break;

@@ -98,7 +98,9 @@ class CudaMultiLineFastaBuffer:
 
     @property
     def n_lines(self) -> int:
-        return self._line_starts.numel()
+        # the reference keeps new_lines[:new_entries[-1]] (multiline_buffer.py:99-101): the newline that precedes the
+        # next entry's header is not counted
+        return max(self._line_starts.numel() - 1, 0)
 
     @property
     def data(self):

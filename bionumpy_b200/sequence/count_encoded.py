@@ -86,6 +86,16 @@ def _labels_of(encoding):
     return encoding.get_labels()
 
 
+def _check_range(flat, n_bins):
+    """np.bincount(values, minlength=len(alphabet)) of the reference (count_encoded.py:173-177) raises on negative
+    values and would grow the table for codes beyond the alphabet; the kernels fold with a modulo (that is the
+    count_hashed extension), so out-of-range codes are an error here instead of a plausible wrong histogram."""
+    if flat.numel():
+        lo, hi = int(flat.min().item()), int(flat.max().item())
+        if lo < 0 or hi >= n_bins:
+            raise ValueError(f"count_encoded: value {lo if lo < 0 else hi} outside the alphabet (0..{n_bins - 1})")
+
+
 def count_encoded(values, weights=None, axis: int = -1) -> EncodedCounts:
     """count_encoded.py:150-188.  axis=None: flattened counts; axis=-1: one row of counts per row."""
     if weights is not None:
@@ -99,10 +109,12 @@ def count_encoded(values, weights=None, axis: int = -1) -> EncodedCounts:
         values = values.ravel()
     if isinstance(values, EncodedArray) and values.ndim == 1:
         flat = values.raw().contiguous().to(torch.int64)
+        _check_range(flat, n_bins)
         hist, status = ops.bincount(flat, n_bins)
         return EncodedCounts(alphabet, hist)
     if axis in (-1, 1) and isinstance(values, EncodedRaggedArray):
         flat = values.ravel().raw().contiguous().to(torch.int64)
+        _check_range(flat, n_bins)
         offsets = ops.row_offsets(values.lengths.contiguous(), 0)
         out, status = ops.bincount_rows(flat, offsets, n_bins)
         return EncodedCounts(alphabet, out)

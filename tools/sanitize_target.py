@@ -18,5 +18,12 @@ for chunk_np in (o.synthetic_fastq(0, 3000), make_fastq(rng, 300, 0, 400, lower_
     h, _, _ = ops.rows_kmer_hash(chunk, starts, lens, 0, 31)
     m, _, _ = ops.rows_minimizers(chunk, starts, lens, 0, 31, 41)
     c, _, _ = ops.rows_encode(chunk, starts, lens, 0)
+    hc, _, _ = ops.rows_kmer_hash_canonical(chunk, starts, lens, 0, 21, 3)
+    lut = torch.arange(256, dtype=torch.uint8, device="cuda")
+    rc, _ = ops.rows_reverse_complement(chunk, starts, lens, lut)
+# a tile with more newlines than the list holds (the row warps rebuild it window by window)
+tiny = torch.from_numpy(make_fastq(rng, 3000, 0, 3)).cuda()
+want, _, _ = o.fastq_chunk_kmer_counts(tiny.cpu().numpy(), 2, 16, False)
+assert np.array_equal(ops.chunk_kmer_count(tiny, 2, 16)[0].cpu().numpy(), want)
 torch.cuda.synchronize()
 print("sanitize target ok")
