@@ -213,6 +213,45 @@ __global__ void __launch_bounds__(256) bincount_rows_kernel(const int64_t *value
 
 
 // ------------------------------------------------------------------------------------------
+// Multi-line FASTA bookkeeping (io/multiline_buffer.py:46-62,89-106) over the per-line (start, len) arrays of K1:
+//   flags    : is the line a header ('>'), does an entry start right after its newline, '\r' trimming;
+//              out[0] = max index of a line that is followed by an entry start + 1 (0: none), out[1] = 1 if one of the
+//              first ten lines ends in '\r'
+//   entries  : with hdr_before = exclusive scan of the header flags (bnpk_row_offsets): header fields, the compacted
+//              sequence-line list and the per-entry sequence lengths
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) multiline_flags_kernel(const uint8_t *chunk, size_t n, const int64_t *starts, const int32_t *lens,
+                                                              size_t n_lines, int32_t *is_header, int64_t *out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += (size_t)gridDim.x * blockDim.x) {
+        const int64_t s = starts[i], e = s + lens[i];                 // e = position of the line's '\n'
+        is_header[i] = (i == 0 || chunk[s] == '>') ? 1 : 0;
+        const size_t nxt = (size_t)min((long long)(e + 1), (long long)n - 1);
+        if (chunk[nxt] == '>') atomicMax((unsigned long long *)&out[0], (unsigned long long)i + 1ull);
+        if (i < 10 && e > 0 && chunk[e - 1] == 13) out[1] = 1;
+    }
+}
+__global__ void __launch_bounds__(256) multiline_entries_kernel(const uint8_t *chunk, const int64_t *starts, const int32_t *lens,
+                                                                const int32_t *is_header, const int64_t *hdr_before, size_t keep,
+                                                                int trim_cr, int64_t *h_starts, int32_t *h_lens, int64_t *s_starts,
+                                                                int32_t *s_lens, unsigned long long *entry_lens) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < keep; i += (size_t)gridDim.x * blockDim.x) {
+        const int64_t s = starts[i];
+        int32_t L = lens[i];
+        if (trim_cr && L > 0 && chunk[s + L - 1] == 13) L -= 1;       // _modify_ends_for_carriage_returns (:103-106)
+        const int64_t e = hdr_before[i] + is_header[i] - 1;           // entry of this line
+        if (is_header[i]) {
+            h_starts[e] = s + 1;
+            h_lens[e] = max(L - 1, 0);
+        } else {
+            const int64_t pos = (int64_t)i - (e + 1);                 // sequence lines before this one
+            s_starts[pos] = s;
+            s_lens[pos] = L;
+            atomicAdd(entry_lens + e, (unsigned long long)L);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Indexed FASTA (io/indexed_fasta.py:101-206): sequence positions -> file bytes, skipping the line ends.
 // Row r = bases [row_start[r], row_start[r] + row_len[r]) of the contig whose first base is file byte
 // contig_offset[r], written with lenc[r] bases per line of lenb[r] bytes.  One warp per row, coalesced writes.
@@ -422,6 +461,27 @@ int bnpk_bincount_rows(const int64_t *values, const int64_t *offsets, size_t n_r
     bincount_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(values, offsets, n_rows, (uint64_t)n_bins,
                                                                  (unsigned long long *)out, status);
     BNPK_LAUNCHED("bincount_rows_kernel");
+    return 0;
+}
+
+int bnpk_multiline_flags(const uint8_t *chunk, size_t n, const int64_t *line_starts, const int32_t *line_lens, size_t n_lines,
+                         int32_t *is_header, int64_t *out2, void *stream) {
+    if (n_lines == 0 || n == 0) return 0;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n_lines + 255) / 256, (size_t)sm_count() * 8));
+    multiline_flags_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunk, n, line_starts, line_lens, n_lines, is_header, out2);
+    BNPK_LAUNCHED("multiline_flags_kernel");
+    return 0;
+}
+
+int bnpk_multiline_entries(const uint8_t *chunk, const int64_t *line_starts, const int32_t *line_lens, const int32_t *is_header,
+                           const int64_t *hdr_before, size_t keep, int trim_cr, int64_t *h_starts, int32_t *h_lens,
+                           int64_t *s_starts, int32_t *s_lens, int64_t *entry_lens, void *stream) {
+    if (keep == 0) return 0;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((keep + 255) / 256, (size_t)sm_count() * 8));
+    multiline_entries_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunk, line_starts, line_lens, is_header, hdr_before, keep, trim_cr,
+                                                                     h_starts, h_lens, s_starts, s_lens,
+                                                                     (unsigned long long *)entry_lens);
+    BNPK_LAUNCHED("multiline_entries_kernel");
     return 0;
 }
 

@@ -33,7 +33,8 @@ _POOL = None
 def _pool():
     global _POOL
     if _POOL is None:
-        n = max(4, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)))
+        n = int(os.environ.get("BNP_INGEST_THREADS", "0")) or \
+            max(4, min(48, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)))
         _POOL = ThreadPoolExecutor(n, thread_name_prefix="bnp-ingest")
     return _POOL
 
@@ -77,7 +78,7 @@ class _PreadSource(_Source):
         nbytes = max(0, min(nbytes, self._size - self._pos))
         buf = self._staging.take(nbytes)
         mv = memoryview(buf.numpy())
-        piece = max(1 << 20, -(-nbytes // 16))
+        piece = max(1 << 20, min(8 << 20, -(-nbytes // 32)))
         futs = []
         for a in range(0, nbytes, piece):
             b = min(nbytes, a + piece)

@@ -6,8 +6,8 @@
   get_data        : headers are (chunk, starts, lens) views; the sequence lines of each entry are joined by the
                     row-driven copy kernel (K2 with an identity LUT) -- the reference's boolean-mask gather
                     (multiline_buffer.py:46-62) -- giving one contiguous row per entry.
-Per-line index arithmetic (which line belongs to which entry, entry lengths) is a handful of torch ops on the
-per-line arrays; bytes are only touched by the CUDA kernels."""
+The per-line bookkeeping (which line is a header, which entry a line belongs to, entry lengths, the compacted list of
+sequence lines) is two small kernels and a device scan (bnpk_multiline_flags, bnpk_row_offsets, bnpk_multiline_entries)."""
 import torch
 
 from .. import _native as nv
@@ -33,10 +33,13 @@ class CudaMultiLineFastaBuffer:
     dataclass = SequenceEntry
     SKIP_LAZY = True
 
-    def __init__(self, data, line_starts, line_lens, is_header):
+    def __init__(self, data, line_starts, line_lens, is_header, trim_cr=False):
         self._data = data                    # device bytes, complete entries only
         self._line_starts, self._line_lens, self._is_header = line_starts, line_lens, is_header
-        self._n_entries = int(is_header.sum().item())
+        self._trim_cr = trim_cr
+        # entry index of every line = headers before it (device scan, K-row_offsets); the total is the entry count
+        self._hdr_before = ops.row_offsets(is_header.contiguous(), 0)
+        self._n_entries = int(self._hdr_before[-1].item())
         self._cache = None
 
     # ---- protocol ---------------------------------------------------------------------------------
@@ -71,26 +74,17 @@ class CudaMultiLineFastaBuffer:
         assert chunk.numel() and int(chunk[0].item()) == ord(">"), "multi-line FASTA chunk must start with '>'"
         starts, lens = cls._lines(chunk)
         n_lines = starts.numel()
-        # a new entry starts after newline i iff the byte after it is '>' (multiline_buffer.py:93);
-        # that byte is the first byte of line i+1, or the chunk's last byte for the final newline
-        line_ends = starts + lens.to(torch.int64)                    # position of each line's '\n'
-        next_is_hdr = chunk[(line_ends + 1).clamp(max=chunk.numel() - 1)] == ord(">")
-        entry_after = torch.nonzero(next_is_hdr).reshape(-1)         # newline indices that precede an entry start
-        if entry_after.numel() == 0:
+        # header flags, the last newline that is followed by an entry start (multiline_buffer.py:93), '\r' probe: one kernel
+        is_header = torch.empty(n_lines, dtype=torch.int32, device=chunk.device)
+        out2 = torch.zeros(2, dtype=torch.int64, device=chunk.device)
+        with torch.cuda.device(chunk.device):
+            nv.check(nv.lib().bnpk_multiline_flags(nv.ptr(chunk), chunk.numel(), nv.ptr(starts), nv.ptr(lens), n_lines,
+                                                   nv.ptr(is_header), nv.ptr(out2), nv.stream_ptr()))
+        keep, has_cr = (int(x) for x in out2.cpu().tolist())          # the one synchronisation of this buffer
+        if keep == 0:
             raise IncompleteEntryException("No complete entry found in multi-line FASTA buffer")
-        last_nl = int(entry_after[-1].item())
-        size = int(line_ends[last_nl].item()) + 1                    # start of the last (incomplete) entry
-        keep = last_nl + 1                                           # lines 0..last_nl are complete
-        starts, lens = starts[:keep], lens[:keep]
-        # '\r' trimming like _modify_ends_for_carriage_returns (:103-106): decided on the first ten lines
-        ends = starts + lens.to(torch.int64)
-        probe = ends[:10]
-        if bool(((chunk[(probe - 1).clamp(min=0)] == 13) & (probe > 0)).any().item()):
-            has_cr = (chunk[(ends - 1).clamp(min=0)] == 13) & (lens > 0)
-            lens = lens - has_cr.to(torch.int32)
-        is_header = chunk[starts] == ord(">")
-        is_header[0] = True
-        return cls(chunk[:size], starts, lens, is_header)
+        size = int((starts[keep - 1] + lens[keep - 1]).item()) + 1      # start of the last (incomplete) entry
+        return cls(chunk[:size], starts[:keep], lens[:keep], is_header[:keep], bool(has_cr))
 
     @property
     def size(self) -> int:
@@ -114,17 +108,21 @@ class CudaMultiLineFastaBuffer:
 
     def _materialise(self):
         if self._cache is None:
-            hdr = self._is_header
-            h_starts = (self._line_starts[hdr] + 1).contiguous()
-            h_lens = (self._line_lens[hdr] - 1).clamp(min=0).contiguous()
-            seq = ~hdr
-            s_starts = self._line_starts[seq].contiguous()
-            s_lens = self._line_lens[seq].contiguous()
-            # entry of every sequence line, entry lengths = sums of their line lengths
-            entry_of_line = (torch.cumsum(hdr.to(torch.int64), 0) - 1)[seq]
-            entry_lens = torch.zeros(self._n_entries, dtype=torch.int64, device=self._data.device)
-            entry_lens.index_add_(0, entry_of_line, s_lens.to(torch.int64))
-            flat, _, _ = ops.rows_encode(self._data, s_starts, s_lens, nv.ENC_LUT, _identity_lut(self._data.device))
+            dev = self._data.device
+            keep, n_e = self._line_starts.numel(), self._n_entries
+            n_seq = keep - n_e
+            h_starts = torch.empty(n_e, dtype=torch.int64, device=dev)
+            h_lens = torch.empty(n_e, dtype=torch.int32, device=dev)
+            s_starts = torch.empty(n_seq, dtype=torch.int64, device=dev)
+            s_lens = torch.empty(n_seq, dtype=torch.int32, device=dev)
+            entry_lens = torch.zeros(n_e, dtype=torch.int64, device=dev)
+            starts, lens, hdr = self._line_starts.contiguous(), self._line_lens.contiguous(), self._is_header.contiguous()
+            with torch.cuda.device(dev):
+                nv.check(nv.lib().bnpk_multiline_entries(nv.ptr(self._data), nv.ptr(starts), nv.ptr(lens), nv.ptr(hdr),
+                                                         nv.ptr(self._hdr_before), keep, int(self._trim_cr), nv.ptr(h_starts),
+                                                         nv.ptr(h_lens), nv.ptr(s_starts), nv.ptr(s_lens), nv.ptr(entry_lens),
+                                                         nv.stream_ptr()))
+            flat, _, _ = ops.rows_encode(self._data, s_starts, s_lens, nv.ENC_LUT, _identity_lut(dev))
             names = FieldView(self._data, h_lens, h_starts)
             seqs = EncodedRaggedArray(EncodedArray(flat, BaseEncoding), entry_lens.to(torch.int32))
             self._cache = (names, seqs)

@@ -222,6 +222,19 @@ int bnpk_fasta_gather(const uint8_t *file, size_t file_bytes, size_t n_rows, con
                       const int64_t *row_start, const int64_t *row_len, const int32_t *lenc, const int32_t *lenb,
                       const int64_t *out_offsets, uint8_t *out, int64_t *status, void *stream);
 
+/* Multi-line FASTA bookkeeping over the per-line arrays of bnpk_line_split(lines_per_entry = 1)
+ * (MultiLineFastaBuffer.from_raw_buffer / get_data, io/multiline_buffer.py:46-62,89-106):
+ *   bnpk_multiline_flags    is_header[i] (line starts with '>'), out2[0] = 1 + the last line whose newline is followed by
+ *                           '>' (0: no complete entry), out2[1] = 1 if one of the first ten lines ends in '\r'
+ *   bnpk_multiline_entries  with hdr_before = bnpk_row_offsets(is_header, 0): header fields (h_starts/h_lens per entry),
+ *                           the sequence lines compacted in order (s_starts/s_lens) and entry_lens (zero-initialised by
+ *                           the caller) = bases per entry; trim_cr as decided from out2[1]. */
+int bnpk_multiline_flags(const uint8_t *chunk, size_t n, const int64_t *line_starts, const int32_t *line_lens, size_t n_lines,
+                         int32_t *is_header, int64_t *out2, void *stream);
+int bnpk_multiline_entries(const uint8_t *chunk, const int64_t *line_starts, const int32_t *line_lens, const int32_t *is_header,
+                           const int64_t *hdr_before, size_t keep, int trim_cr, int64_t *h_starts, int32_t *h_lens,
+                           int64_t *s_starts, int32_t *s_lens, int64_t *entry_lens, void *stream);
+
 /* Bloom filter over k-mer hashes (sequence/bloom_filter.py:15-42): hash function i is v ^ offsets[i]; the filter is
  * one byte per position (the reference's bool mask).  insert: mask[(v ^ offsets[i]) % mask_size] = 1 for every value and
  * function; query: out[j] = AND over the functions. */
