@@ -188,5 +188,7 @@ constexpr int64_t kScratch32MaxBins = 1ll << 24;   // 64 MiB of u32 counters at 
 int launch_tma_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st);
 // the warp-specialised fused count (tile_ws_kernel.cu): same eligibility, the default
 int launch_ws_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st);
+bool wsm_count_eligible(const TileArgs &a, bool smem_hist);
+int launch_wsm_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st);
 
 }  // namespace bnpk
