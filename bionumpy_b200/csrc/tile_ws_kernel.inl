@@ -86,11 +86,11 @@ constexpr int kOffBar = (kOffDesc + kNS * kDescWords * 4 + 7) & ~7;   // full | 
 constexpr int kOffWsum = kOffBar + 3 * kNS * 8;               // [group][2][kSW]
 constexpr int kOffQueue = kOffWsum + kSG * 2 * kSW * 4;       // [kQN] entries, then the head counter
 constexpr int kOffLut = (kOffQueue + kQN * 4 + 16 + 15) & ~15;
-// minimizer build: per row warp, kMinzW positions x 32 lanes x 8 bytes -- the hashes of the current block of W k-mers,
+// minimizer build: per row warp, kMinzW + 1 positions x 32 lanes x 8 bytes -- the hashes of the current block of W k-mers,
 // turned into the block's suffix minima in place (two-level block minima; one lane per row, lanes in lock-step)
 constexpr int kMinzW = 16;                      // longest window (in k-mers) this build takes
 constexpr int kOffMinz = (kOffLut + 256 + 127) & ~127;
-constexpr int kFixedBytes = kOffMinz + (MINZ ? kRW * kMinzW * 32 * 8 : 0);
+constexpr int kFixedBytes = kOffMinz + (MINZ ? kRW * (kMinzW + 1) * 256 : 0);   // + the all-ones position
 static_assert(kOffBar % 8 == 0 && kOffLut % 16 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -223,6 +223,14 @@ __device__ __forceinline__ void emit_positions2(uint64_t m0, uint32_t li0, uint3
     }
 }
 
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t lo, uint32_t hi) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
+    return ((uint64_t)hi << 32) | lo;
+}
 // bins that are not a power of two: out of line, the callers' loops stay small
 __device__ __noinline__ uint64_t mod_bins(uint64_t h, uint64_t n_bins) { return h % n_bins; }
 
@@ -529,6 +537,11 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
         }
     } else {
         // ============================ R: rows -> codes -> k-mers -> histogram =================================
+        if constexpr (MINZ) {                                         // the all-ones position behind every window length
+            for (int p = 0; p <= kMinzW; ++p)
+                sts64(smem_addr(s_fixed + kOffMinz) + (uint32_t)((warp - kRWarp0) * ((kMinzW + 1) * 256) + 256 * p + 8 * lane), 0xFFFFFFFFu, 0xFFFFFFFFu);
+            __syncwarp();
+        }
         const bool cr = a.status[BNPK_ST_CR] != 0;
         const uint64_t hmask = (a.n_bins & (a.n_bins - 1)) == 0 ? a.n_bins - 1 : 0;
         const uint64_t kmask = (1ull << (2 * a.k)) - 1;
@@ -677,49 +690,54 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                     // block is complete.  The position is the same in every lane (all rows start at k-mer 0), so every branch
                     // below is warp-uniform; lanes past their row's end count into nothing.
                     const int W = a.window - a.k + 1;
-                    uint2 *mb = reinterpret_cast<uint2 *>(s_fixed + kOffMinz) + (warp - kRWarp0) * (kMinzW * 32) + lane;
+                    // 32-bit shared addresses: position p of my lane is mb0 + 256 p; position W holds all ones for good (the
+                    // "suffix" the last position of a block asks for: none)
+                    const uint32_t mb0 = smem_addr(s_fixed + kOffMinz) + (uint32_t)((warp - kRWarp0) * ((kMinzW + 1) * 256) + 8 * lane);
+                    const uint32_t mb_end = mb0 + 256u * (uint32_t)W;
                     const int maxnpos = __reduce_max_sync(0xffffffffu, npos);
                     const int nblk = (maxnpos + 15) >> 4;
+                    const uint32_t nout = (uint32_t)max(npos - W + 1, 0);   // windows of my row
                     uint32_t w0 = enc_masked(0), w1 = enc_masked(1), w2 = enc_masked(2);
-                    int r = 0;
-                    uint64_t pre = 0, sfx_next = ~0ull;               // sfx_next: the previous block's suffix minimum the NEXT
-                                                                      // step needs, loaded a step ahead (all ones: none)
+                    uint32_t mb_r = mb0, ic = (uint32_t)(1 - W);      // ic: index of the window that ends at this step
+                    uint64_t pre = ~0ull, sfx_next = ~0ull;           // sfx_next: the previous block's suffix minimum this step
+                                                                      // needs, loaded a step ahead
                     for (int b = 0; b < nblk; ++b) {
                         const uint32_t w3 = enc_masked(b + 3);
                         const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
                         const int tn = min(16, maxnpos - 16 * b);
 #pragma unroll 2
                         for (int t = 0; t < tn; ++t) {                // compact on purpose: unrolled 16 times the loop does not
-                            const int i = 16 * b + t;                 // fit the instruction cache (12.3 ms)
-                            const uint32_t lo32 = __funnelshift_r(a0, a1, 2 * t), hi32 = __funnelshift_r(a1, a2, 2 * t);
-                            const uint64_t h = (((uint64_t)hi32 << 32) | lo32) & kmask;
-                            mb[r * 32] = make_uint2((uint32_t)h, (uint32_t)(h >> 32));
-                            pre = (r == 0 || h < pre) ? h : pre;
+                            const uint32_t lo32 = __funnelshift_r(a0, a1, 2 * t) & (uint32_t)kmask;   // fit the instruction cache
+                            const uint32_t hi32 = __funnelshift_r(a1, a2, 2 * t) & (uint32_t)(kmask >> 32);
+                            const uint64_t h = ((uint64_t)hi32 << 32) | lo32;
+                            sts64(mb_r, lo32, hi32);
+                            pre = h < pre ? h : pre;
                             const uint64_t m = sfx_next < pre ? sfx_next : pre;   // before the first full window: not counted
                             const uint64_t bb = hmask ? (m & hmask) : mod_bins(m, a.n_bins);
-                            const bool mine = i >= W - 1 && i < npos;
+                            const bool mine = ic < nout;
                             if constexpr (SMEM_HIST) hist_add_val(hist_sa + 4u * (uint32_t)bb, mine ? 1u : 0u);
                             else if (mine) {
                                 if constexpr (HIST == 2) atomicAdd(a.hist32 + bb, 1u);
                                 else atomicAdd(a.hist + bb, 1ull);
                             }
-                            if (++r == W) {                           // block complete: its suffix minima, in place; every
-                                r = 0;                                // load is issued one element ahead of its use
-                                uint64_t sfx = ~0ull;
-                                uint2 nx = mb[(W - 1) * 32];
-                                for (int q = W - 1; q >= 1; --q) {
-                                    const uint64_t v = ((uint64_t)nx.y << 32) | nx.x;
-                                    if (q > 1) nx = mb[(q - 1) * 32];
+                            ++ic;
+                            mb_r += 256u;
+                            if (mb_r == mb_end) {                     // block complete: its suffix minima, in place; every
+                                uint64_t sfx = ~0ull;                 // load is issued one element ahead of its use
+                                uint32_t q = mb_end - 256u;
+                                uint64_t nx = lds64(q);
+                                for (; q > mb0; q -= 256u) {
+                                    const uint64_t v = nx;
+                                    if (q > mb0 + 256u) nx = lds64(q - 256u);
                                     sfx = v < sfx ? v : sfx;
-                                    mb[q * 32] = make_uint2((uint32_t)sfx, (uint32_t)(sfx >> 32));
+                                    sts64(q, (uint32_t)sfx, (uint32_t)(sfx >> 32));
                                 }
-                                sfx_next = W > 1 ? sfx : ~0ull;       // suffix 1.. of the block: what position 0 needs
-                            } else if (r + 1 < W) {                   // index r+1 still holds the previous block's suffix
-                                const uint2 sv = mb[(r + 1) * 32];
-                                sfx_next = i >= W - 1 ? (((uint64_t)sv.y << 32) | sv.x) : ~0ull;
+                                sfx_next = sfx;                       // suffix 1.. of the block: what position 0 needs (W = 1: none)
+                                mb_r = mb0;
+                                pre = ~0ull;
                             } else {
-                                sfx_next = ~0ull;                     // the block's last position: the window is the block
-                            }
+                                sfx_next = lds64(mb_r + 256u);        // still the previous block's (garbage before there is one:
+                            }                                         // those windows are not counted)
                         }
                         w0 = w1;
                         w1 = w2;
