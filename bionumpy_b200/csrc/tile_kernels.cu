@@ -513,7 +513,7 @@ static bool tma_kernel_allowed() { return tile_kernel_choice() != 0; }
 
 static int launch_count(const TileArgs &a, int enc_mode, bool smem_hist, cudaStream_t st) {
     if (tma_kernel_allowed() && tile_kernel_choice() != 1 && wsm_count_eligible(a, smem_hist))
-        return launch_wsm_count(a, enc_mode, smem_hist, st);          // minimizers, windows of up to 16 k-mers
+        return launch_wsm_count(a, enc_mode, smem_hist, st);          // minimizers, windows of up to 12 k-mers
     if (tma_kernel_allowed() && tma_count_eligible(a, smem_hist))
         // the warp-specialised kernel for CTA-private tables; global tables are bound by L2 atomics, where the round-1
         // kernel's 21 row warps per SM keep more of them in flight (2^24 bins: 6.6 ms against 9.3 ms)

@@ -4,17 +4,23 @@
 // k-mer counts: the dominant kernel of the hot path
 #define BNPK_WS_NAMESPACE ws
 #define BNPK_WS_NS 8
+#define BNPK_WS_SG 2
+#define BNPK_WS_RW 8
 #define BNPK_WS_MINZ 0
 #define BNPK_WS_LAUNCH launch_ws_count
 #include "tile_ws_kernel.inl"
 #undef BNPK_WS_NAMESPACE
 #undef BNPK_WS_NS
+#undef BNPK_WS_SG
+#undef BNPK_WS_RW
 #undef BNPK_WS_MINZ
 #undef BNPK_WS_LAUNCH
 
-// minimizer counts (windows of up to 16 k-mers, CTA-private table)
+// minimizer counts (windows of up to 12 k-mers, CTA-private table)
 #define BNPK_WS_NAMESPACE wsm
 #define BNPK_WS_NS 6
+#define BNPK_WS_SG 1       // the row warps bound this build: one scan group is enough, its four warps' worth of
+#define BNPK_WS_RW 12      // threads go to four more row warps
 #define BNPK_WS_MINZ 1
 #define BNPK_WS_LAUNCH launch_wsm_count
 #include "tile_ws_kernel.inl"

@@ -24,7 +24,7 @@
 // sequence/count_encoded.py:173-177 in one pass over the chunk bytes.
 // This file is the body of the kernel: tile_ws_kernel.cu includes it twice -- as namespace ws (k-mer counts, 8 ring
 // slots) and as namespace wsm (minimizer counts: 6 ring slots, the other two's shared memory holds the row warps'
-// sliding-minimum buffers).  BNPK_WS_NAMESPACE, BNPK_WS_NS, BNPK_WS_MINZ and BNPK_WS_LAUNCH are set by the includer.
+// sliding-minimum buffers).  BNPK_WS_NAMESPACE, BNPK_WS_NS, BNPK_WS_SG, BNPK_WS_RW, BNPK_WS_MINZ and BNPK_WS_LAUNCH are set by the includer.
 
 // Development knobs (switch parts of the row warps' work off, per-stage clocks): compiled in only with
 // -DBNPK_WS_DEBUG_KNOBS (tools/dbg_sweep.sh, tools/stage_times.py); production builds fold them away.
@@ -50,10 +50,10 @@ constexpr int kRowMax = 1024;                   // longer rows go to the deferre
 constexpr int kMaxBins = 16384;
 constexpr uint32_t kNoCross = 0xFFFFFFFFu;
 constexpr int kSW = 4;                          // warps of a scan group: 4 KiB of the tile each, 128 B per lane
-constexpr int kSG = 2;                          // scan groups; kNS % kSG == 0: a slot always belongs to the same group (a group must
+constexpr int kSG = BNPK_WS_SG;                        // scan groups; kNS % kSG == 0: a slot always belongs to the same group (a group must
                                                 // never wait for a slot's phase u+1 before phase u completed: mbarrier parity waits
                                                 // cannot tell two phases apart)
-constexpr int kRW = 8;                          // row warps
+constexpr int kRW = BNPK_WS_RW;                        // row warps
 constexpr int kQN = 64;                         // entries of the chunk queue
 // warp ids: the SM arbiter favours the highest id among the ready warps, and a warp that spins on an mbarrier is
 // always ready -- so the consumers come last: P (0) < S (1 ..) < R < F.  (With the scan warps on top, their wait for
@@ -88,7 +88,7 @@ constexpr int kOffQueue = kOffWsum + kSG * 2 * kSW * 4;       // [kQN] entries, 
 constexpr int kOffLut = (kOffQueue + kQN * 4 + 16 + 15) & ~15;
 // minimizer build: per row warp, kMinzW + 1 positions x 32 lanes x 8 bytes -- the hashes of the current block of W k-mers,
 // turned into the block's suffix minima in place (two-level block minima; one lane per row, lanes in lock-step)
-constexpr int kMinzW = 16;                      // longest window (in k-mers) this build takes
+constexpr int kMinzW = 12;                      // longest window (in k-mers) this build takes
 constexpr int kOffMinz = (kOffLut + 256 + 127) & ~127;
 constexpr int kFixedBytes = kOffMinz + (MINZ ? kRW * (kMinzW + 1) * 256 : 0);   // + the all-ones position
 static_assert(kOffBar % 8 == 0 && kOffLut % 16 == 0, "alignment");
@@ -568,10 +568,12 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
             uint32_t idx = 0;
             if (lane == 0) idx = atomicAdd(s_qhead, 1u);
             idx = __shfl_sync(0xffffffffu, idx, 0);
-            // One-word messages: the producer stores a tagged record, the consumer polls the word and clears it (plain
-            // volatile accesses + fences -- racecheck reports exactly these two lines as a WAR hazard, by design; doing
-            // it with shared-memory atomics is clean under racecheck but slows the kernel from 1.53 to 2.0 ms: the polls
-            // then queue behind the histogram atomics).
+            // One-word messages: the producer fences and stores a tagged record, the consumer polls the word, clears it and
+            // fences (volatile accesses + fence.acq_rel.cta on both sides).  compute-sanitizer's racecheck follows
+            // bar.sync / __syncwarp only: it reports these two lines and every access that is ordered THROUGH this
+            // hand-off or through the mbarriers (list, descriptor, slot bytes) as hazards
+            // (profiles/r02_compute_sanitizer.txt lists them).  Polling with shared-memory atomics instead slowed the kernel
+            // from 1.53 to 2.0 ms (the polls queue behind the histogram atomics) and silences only these two lines.
             volatile uint32_t *qe = s_queue + (idx & (kQN - 1));
             uint32_t rec = *qe;
             while ((rec >> 16) != (idx & 0x7FFFu) + 1u) {

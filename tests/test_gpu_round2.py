@@ -278,3 +278,37 @@ def test_kmer_index_and_bloom_filter(bnp):
     got = bf[torch.from_numpy(probe).cuda()].cpu().numpy()
     assert np.array_equal(got, oracle.bloom_filter_query(mask, probe, offsets))
     assert bool(bf[kmers.raw().ravel()].all().item())
+
+
+@pytest.mark.parametrize("k,bins,window", [(31, 1 << 14, 42), (31, 1 << 14, 43), (7, 100, 12), (16, 4096, 20), (3, 64, 3), (31, 1 << 14, 31)])
+def test_minimizer_counts_lane_per_row_kernel(bnp, k, bins, window):
+    """Minimizer counts (sequence/minimizers.py:8-17,50-54) through the warp-specialised build (windows of up to 12
+    k-mers, one lane per row, two-level block minima) and, one k-mer beyond, through the older kernel: ragged rows
+    (empty, shorter than the window, longer than a tile), lower case, \\r\\n, a table that is not a power of two."""
+    from bionumpy_b200 import ops
+    rng = np.random.default_rng(5)
+    for chunk in (make_fastq(rng, 700, 0, 400, lower_frac=0.3), make_fastq(rng, 40, 1500, 20000), make_fastq(rng, 3000, 0, 12),
+                  make_fastq(rng, 500, 100, 160, cr=True), oracle.synthetic_fastq(3, 4000)):
+        want, size, n_bases = oracle_hist(chunk, k, bins, window)
+        hist, status = ops.chunk_kmer_count(torch.from_numpy(chunk).cuda(), k, bins, window_size=window)
+        st = ops.read_status(status)
+        assert st.n_complete_bytes == size and st.n_bases == n_bases and st.n_values == want.sum()
+        assert np.array_equal(hist.cpu().numpy(), want)
+
+
+def test_minimizer_counts_dense_newlines(bnp):
+    """Thousands of newlines per tile: the row warp rebuilds the newline list window by window (minimizer build)."""
+    from bionumpy_b200 import ops
+    rng = np.random.default_rng(22)
+    parts = []
+    for _ in range(20000):
+        L = int(rng.integers(0, 6))
+        seq = "".join(rng.choice(list("ACGT"), size=L)) if L else ""
+        parts.append(f"@\n{seq}\n+\n{'I' * L}\n")
+    chunk = np.frombuffer("".join(parts).encode("ascii"), dtype=np.uint8).copy()
+    for k, bins, window in ((1, 4, 2), (2, 16, 4), (2, 1 << 14, 2)):
+        want, size, n_bases = oracle_hist(chunk, k, bins, window)
+        hist, status = ops.chunk_kmer_count(torch.from_numpy(chunk).cuda(), k, bins, window_size=window)
+        st = ops.read_status(status)
+        assert (st.n_records, st.n_complete_bytes, st.n_bases) == (20000, size, n_bases)
+        assert np.array_equal(hist.cpu().numpy(), want)

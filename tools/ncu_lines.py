@@ -42,7 +42,7 @@ for (loc, _), r in zip(seq, data):
     agg[loc][0] += c; agg[loc][1] += s
 print(f"kernel {sub}: {tot} warp-instructions, {tots} samples, {len(seq)} SASS instructions")
 src = {}
-for f in ("tile_kernels.cu", "tile_tma_kernel.cu", "tile_ws_kernel.cu", "tile_common.cuh", "bnpk_device.cuh", "row_kernels.cu", "misc_kernels.cu"):
+for f in ("tile_kernels.cu", "tile_tma_kernel.cu", "tile_ws_kernel.cu", "tile_ws_kernel.inl", "tile_common.cuh", "bnpk_device.cuh", "row_kernels.cu", "misc_kernels.cu"):
     src[f] = open(os.path.join(root, "bionumpy_b200", "csrc", f)).read().split("\n")
 for loc, (c, s) in sorted(agg.items(), key=lambda x: -x[1][0])[:top_n]:
     f, ln = loc if loc else ("?", 0)

@@ -10,7 +10,7 @@ rng = np.random.default_rng(0)
 for chunk_np in (o.synthetic_fastq(0, 3000), make_fastq(rng, 300, 0, 400, lower_frac=0.2), make_fastq(rng, 20, 2500, 6000),
                  make_fastq(rng, 2000, 0, 2)):
     chunk = torch.from_numpy(chunk_np).cuda()
-    for k, bins, w in ((31, 1 << 14, 0), (5, 1024, 0), (31, 1 << 20, 0), (15, 4096, 33)):
+    for k, bins, w in ((31, 1 << 14, 0), (5, 1024, 0), (31, 1 << 20, 0), (15, 4096, 33), (31, 1 << 14, 41), (15, 4096, 22)):
         want, size, nb = o.fastq_chunk_kmer_counts(chunk_np, k, bins, bins != 4 ** k, window_size=w)
         hist, st = ops.chunk_kmer_count(chunk, k, bins, window_size=w)
         assert np.array_equal(hist.cpu().numpy(), want)
@@ -25,5 +25,7 @@ for chunk_np in (o.synthetic_fastq(0, 3000), make_fastq(rng, 300, 0, 400, lower_
 tiny = torch.from_numpy(make_fastq(rng, 3000, 0, 3)).cuda()
 want, _, _ = o.fastq_chunk_kmer_counts(tiny.cpu().numpy(), 2, 16, False)
 assert np.array_equal(ops.chunk_kmer_count(tiny, 2, 16)[0].cpu().numpy(), want)
+want, _, _ = o.fastq_chunk_kmer_counts(tiny.cpu().numpy(), 2, 16, False, window_size=3)
+assert np.array_equal(ops.chunk_kmer_count(tiny, 2, 16, window_size=3)[0].cpu().numpy(), want)
 torch.cuda.synchronize()
 print("sanitize target ok")
