@@ -18,7 +18,7 @@
 
 // minimizer counts (windows of up to 12 k-mers, CTA-private table)
 #define BNPK_WS_NAMESPACE wsm
-#define BNPK_WS_NS 6
+#define BNPK_WS_NS 5       // the slots are held for the front end and the encoding only (rows are staged), see kStageU
 #define BNPK_WS_SG 1       // the row warps bound this build: one scan group is enough, its four warps' worth of
 #define BNPK_WS_RW 12      // threads go to four more row warps
 #define BNPK_WS_MINZ 1

@@ -23,7 +23,7 @@
 // Replaces io/one_line_buffer.py:44-71,139-182 + encodings/alphabet_encoding.py:34-46 + sequence/kmers.py:105-126 +
 // sequence/count_encoded.py:173-177 in one pass over the chunk bytes.
 // This file is the body of the kernel: tile_ws_kernel.cu includes it twice -- as namespace ws (k-mer counts, 8 ring
-// slots) and as namespace wsm (minimizer counts: 6 ring slots, the other two's shared memory holds the row warps'
+// slots) and as namespace wsm (minimizer counts: 5 ring slots, the freed shared memory holds the row warps'
 // sliding-minimum buffers).  BNPK_WS_NAMESPACE, BNPK_WS_NS, BNPK_WS_SG, BNPK_WS_RW, BNPK_WS_MINZ and BNPK_WS_LAUNCH are set by the includer.
 
 // Development knobs (switch parts of the row warps' work off, per-stage clocks): compiled in only with
@@ -90,7 +90,11 @@ constexpr int kOffLut = (kOffQueue + kQN * 4 + 16 + 15) & ~15;
 // turned into the block's suffix minima in place (two-level block minima; one lane per row, lanes in lock-step)
 constexpr int kMinzW = 12;                      // longest window (in k-mers) this build takes
 constexpr int kOffMinz = (kOffLut + 256 + 127) & ~127;
-constexpr int kFixedBytes = kOffMinz + (MINZ ? kRW * (kMinzW + 1) * 256 : 0);   // + the all-ones position
+// ... and kStageU code words per lane: rows of up to kStageU units are encoded into them first, the slot goes back to
+// the ring, and the (long) minimizer walk runs on the staged words -- the ring then only has to cover the front end
+constexpr int kStageU = 13;
+constexpr int kOffStage = kOffMinz + (MINZ ? kRW * (kMinzW + 1) * 256 : 0);   // + the all-ones position
+constexpr int kFixedBytes = kOffStage + (MINZ ? kRW * kStageU * 128 : 0);
 static_assert(kOffBar % 8 == 0 && kOffLut % 16 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -613,6 +617,18 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
             const int64_t r_first = q0 + ((base_phase + jr0 + 1u) >> ls);
             const int n_rows_tile = (tile_nl > jr0) ? (int)(((tile_nl - 1u - jr0) >> ls) + 1u) : 0;
 
+            [[maybe_unused]] bool released = false;                   // minimizer build: the chunk gave its slot back early
+            auto release_slot = [&]() {                               // the last chunk of a tile gives its slot back
+                if (lane == 0) {
+                    __threadfence_block();
+                    const uint32_t old = atomicSub(const_cast<uint32_t *>(s_desc + slot * kDescWords + kDRemain), 1u);
+                    if (old == 1u) {
+                        __threadfence_block();
+                        mbar_arrive(bar_free + 8 * slot);
+                    }
+                }
+            };
+
             // 32 rows, one per lane: rows 32*c .. 32*c+31 of the tile; wb = first newline index held by the list
             auto do_chunk = [&](int c, uint32_t wb) {
                 const int s = 32 * c + lane;                          // my row (tile-relative)
@@ -684,6 +700,19 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                 };
                 const uint32_t sh = 2u * o;                           // my row's stream starts at bit 2*o of its first word
 
+                auto report_bad = [&]() {                             // rare: exact position of the first bad byte
+                    for (int pp = b0; pp < e; ++pp) {
+                        const uint32_t cc = sp[pp];
+                        bool okb;
+                        if (ENC == BNPK_ENC_CODES) okb = cc < 4;
+                        else if (ENC == BNPK_ENC_LUT) okb = s_lut[cc] < 4;
+                        else { const uint32_t uu = cc | 0x20u; okb = (uu == 'a' || uu == 'c' || uu == 'g' || uu == 't'); }
+                        if (!okb) {
+                            atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE], (long long)(((r_first + s) << 32) | (int64_t)(pp - b0)));
+                            break;
+                        }
+                    }
+                };
                 if constexpr (MINZ) {
                     // ---- minimizers (sequence/minimizers.py:8-17,50-54): the minimum hash of every window of W consecutive
                     // k-mers, counted.  Two-level block minima: the hashes go in blocks of W; the window that ends at position
@@ -699,12 +728,30 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                     const int maxnpos = __reduce_max_sync(0xffffffffu, npos);
                     const int nblk = (maxnpos + 15) >> 4;
                     const uint32_t nout = (uint32_t)max(npos - W + 1, 0);   // windows of my row
-                    uint32_t w0 = enc_masked(0), w1 = enc_masked(1), w2 = enc_masked(2);
+                    // Rows of up to kStageU units (all rows of the chunk: a warp-uniform choice): every unit is encoded and
+                    // validated now, the words wait in this lane's staging column, and the slot goes back to the ring before
+                    // the walk below, which is many times longer than everything before it.  Longer rows (and the whole-tile
+                    // walk, which owns the slot for all its chunks) read the slot as they go.
+                    const int n_words = max(R, nblk + 3);
+                    const bool stage = chunk_id != kChunkWhole && n_words <= kStageU;
+                    uint32_t *stg = reinterpret_cast<uint32_t *>(s_fixed + kOffStage) + (warp - kRWarp0) * (kStageU * 32) + lane;
+                    if (stage) {
+                        for (int u = 0; u < n_words; ++u) stg[u * 32] = enc_masked(u);
+                        if (badacc) {
+                            report_bad();
+                            badacc = 0;
+                        }
+                        __syncwarp();
+                        release_slot();
+                        released = true;
+                    }
+                    auto word = [&](int u) -> uint32_t { return stage ? stg[u * 32] : enc_masked(u); };
+                    uint32_t w0 = word(0), w1 = word(1), w2 = word(2);
                     uint32_t mb_r = mb0, ic = (uint32_t)(1 - W);      // ic: index of the window that ends at this step
                     uint64_t pre = ~0ull, sfx_next = ~0ull;           // sfx_next: the previous block's suffix minimum this step
                                                                       // needs, loaded a step ahead
                     for (int b = 0; b < nblk; ++b) {
-                        const uint32_t w3 = enc_masked(b + 3);
+                        const uint32_t w3 = word(b + 3);
                         const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
                         const int tn = min(16, maxnpos - 16 * b);
 #pragma unroll 2
@@ -745,7 +792,8 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                         w1 = w2;
                         w2 = w3;
                     }
-                    for (int u = nblk + 3; u < R; ++u) enc_masked(u);   // units no k-mer reaches are still validated
+                    if (!stage)
+                        for (int u = nblk + 3; u < R; ++u) enc_masked(u);   // units no k-mer reaches are still validated
                 } else if (fast) {
                     // A_b = the 16 bases from row position 16b on = funnel(w_b, w_b+1, 2o).  K-mer t of block b is the
                     // field at bit 2t of (A_b, A_b+1); shifted two bits less, (window & mask) is the table's byte offset.
@@ -847,19 +895,7 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                         w2 = w3;
                     }
                 }
-                if (badacc) {                                         // rare: exact position of the first bad byte
-                    for (int pp = b0; pp < e; ++pp) {
-                        const uint32_t cc = sp[pp];
-                        bool okb;
-                        if (ENC == BNPK_ENC_CODES) okb = cc < 4;
-                        else if (ENC == BNPK_ENC_LUT) okb = s_lut[cc] < 4;
-                        else { const uint32_t uu = cc | 0x20u; okb = (uu == 'a' || uu == 'c' || uu == 'g' || uu == 't'); }
-                        if (!okb) {
-                            atomicMin((long long *)&a.status[BNPK_ST_BAD_BASE], (long long)(((r_first + s) << 32) | (int64_t)(pp - b0)));
-                            break;
-                        }
-                    }
-                }
+                if (badacc) report_bad();
             };
 
             if (chunk_id == 0u || chunk_id == kChunkWhole)           // the tile's own checks, once per tile
@@ -944,16 +980,8 @@ __global__ void __launch_bounds__(kCta, 1) tile_ws_kernel(const TileArgs a) {
                 }
             }
             if ((dbg & 16) && lane == 0) atomicAdd((unsigned long long *)(a.ws + 8), (unsigned long long)((uint32_t)clock64() - t_start));
-            // ---- the last chunk of a tile gives its slot back
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                const uint32_t old = atomicSub(const_cast<uint32_t *>(s_desc + slot * kDescWords + kDRemain), 1u);
-                if (old == 1u) {
-                    __threadfence_block();
-                    mbar_arrive(bar_free + 8 * slot);
-                }
-            }
+            if (!released) release_slot();
         }
         const uint64_t sum_bases = warp_sum_u64(acc_bases), sum_values = warp_sum_u64(acc_values);
 #pragma unroll
