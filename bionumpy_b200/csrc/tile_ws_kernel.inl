@@ -23,7 +23,7 @@
 // Replaces io/one_line_buffer.py:44-71,139-182 + encodings/alphabet_encoding.py:34-46 + sequence/kmers.py:105-126 +
 // sequence/count_encoded.py:173-177 in one pass over the chunk bytes.
 // This file is the body of the kernel: tile_ws_kernel.cu includes it twice -- as namespace ws (k-mer counts, 8 ring
-// slots) and as namespace wsm (minimizer counts: 5 ring slots, the freed shared memory holds the row warps'
+// slots) and as namespace wsm (minimizer counts: 4 ring slots, the freed shared memory holds the row warps'
 // sliding-minimum buffers).  BNPK_WS_NAMESPACE, BNPK_WS_NS, BNPK_WS_SG, BNPK_WS_RW, BNPK_WS_MINZ and BNPK_WS_LAUNCH are set by the includer.
 
 // Development knobs (switch parts of the row warps' work off, per-stage clocks): compiled in only with
