@@ -265,3 +265,44 @@ def test_ingest_sources_reproduce_the_bytes(tmp_path):
         assert src.parallel == parallel
         got, sizes = drain(src, 100_003)
         assert got == data and all(s == 100_003 for s in sizes[:-1]), name
+
+
+def _block_minima_model(h, W):
+    """Step-for-step model of the minimizer walk of one lane in csrc/tile_ws_kernel.inl (wsm build): the hashes go in blocks
+    of W; a block's hashes are stored as they come and become suffix minima in place when the block is complete; the
+    window that ends at position r of a block is min(previous block's suffix r+1.., this block's prefix ..r); position W
+    of the buffer holds all ones for good; the suffix a step needs is read at the end of the step before."""
+    ONES = np.uint64(0xFFFFFFFFFFFFFFFF)
+    buf = np.full(W + 1, ONES, dtype=np.uint64)
+    out, r, pre, sfx_next = [], 0, ONES, ONES
+    for i, x in enumerate(h):
+        buf[r] = x
+        pre = min(pre, x)
+        m = min(sfx_next, pre)
+        if i >= W - 1:                      # the kernel counts exactly these (ic < nout)
+            out.append(m)
+        r += 1
+        if r == W:
+            sfx = ONES
+            for q in range(W - 1, 0, -1):
+                sfx = min(sfx, buf[q])
+                buf[q] = sfx
+            sfx_next, r, pre = sfx, 0, ONES
+        else:
+            sfx_next = buf[r + 1]           # previous block's suffix (or stale data before there is one: not counted)
+    return np.array(out, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("W", [1, 2, 3, 5, 11, 12])
+def test_two_level_block_minima_model_matches_window_minimum(W):
+    """The algorithm the minimizer kernel runs per lane, against the definition (sequence/minimizers.py:8-17: the minimum
+    of every window of W consecutive k-mer hashes)."""
+    rng = np.random.default_rng(100 + W)
+    for n in (0, 1, W - 1, W, W + 1, 2 * W, 2 * W + 1, 57, 120, 301):
+        if n < 0:
+            continue
+        h = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+        if n % 3 == 0 and n:
+            h[rng.integers(0, n, size=max(n // 4, 1))] = h[0]          # ties
+        want = np.array([h[j:j + W].min() for j in range(max(n - W + 1, 0))], dtype=np.uint64)
+        assert np.array_equal(_block_minima_model(h, W), want), (W, n)
