@@ -66,3 +66,25 @@ def test_torch_library_registers_the_ops():
         assert hasattr(ops, name), name
     schema = torch._C._get_schema("bnpk::chunk_kmer_count", "")
     assert "Tensor(a!) hist" in str(schema)
+
+
+def test_dominant_kernels_are_sm100a_code_without_spills():
+    """The in-tree library carries sm_100a SASS of both builds of the warp-specialised kernel, within the register budget
+    of their CTA sizes (576 and 704 threads) and without local-memory spills (cuobjdump works without a GPU)."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    blocks = out.split(" Function ")
+    seen = {}
+    for name, regs_max in (("_ZN4bnpk2ws14tile_ws_kernelILi0ELi1EEEvNS_8TileArgsE", 112), ("_ZN4bnpk3wsm14tile_ws_kernelILi0ELi1EEEvNS_8TileArgsE", 88)):
+        blk = next(b for b in blocks if b.startswith(name))
+        m = re.search(r"REG:(\d+) STACK:(\d+)", blk)
+        assert m, blk[:200]
+        seen[name] = (int(m.group(1)), int(m.group(2)))
+        assert int(m.group(1)) <= regs_max and int(m.group(2)) == 0, (name, m.group(0))
+    assert len(seen) == 2
